@@ -1,0 +1,85 @@
+/* kp_b200.h — C ABI of the B200-native stage-1 hot path.
+ *
+ * The reference (YunjiKim/Unsupervised-Keypoint-Learning-for-Guiding-Class-conditional-Video-Prediction)
+ * is pure Python on TensorFlow 1.12 and has NO native/FFI boundary of its own; the arithmetic of the
+ * stage-1 path lives inside TF ops.  Each entry point below therefore cites the *reference call site*
+ * (file:line under /root/reference) whose TF op chain it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; the library never allocates,
+ *     frees or retains device memory (the caller's allocator owns all buffers, including workspaces);
+ *   - tensors are channels-last (NHWC) like the reference's; fp32 at the keypoint boundary;
+ *   - all work is enqueued asynchronously on the caller-supplied cudaStream_t (passed as void*);
+ *   - return value: 0 = ok, <0 = error (KP_ERR_*), message via kp_last_error() (thread-local);
+ *   - no exceptions cross the ABI.
+ */
+#ifndef KP_B200_H
+#define KP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KP_OK 0
+#define KP_ERR_INVALID_ARG (-1)
+#define KP_ERR_UNSUPPORTED (-2)
+#define KP_ERR_CUDA (-3)
+#define KP_ERR_DRIVER (-4)
+
+/* ABI version of this header (bumped on any signature change). */
+int kp_abi_version(void);
+/* Last error message of the calling thread ("" if none). */
+const char* kp_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic; for bench accounting). */
+unsigned long long kp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 — keypoint math (utils/model.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Fused get_coord x2 + stack + get_gaussian_maps.
+ *   replaces: utils/model.py:63-70 (get_coord, twice), models/networks/__init__.py:68-71 (stack (x,y)),
+ *             utils/model.py:49-60 (get_gaussian_maps) as called from
+ *             models/detector_translator_model.py:166-169.
+ *   logits [B,H,W,K] f32 -> mu [B,K,2] f32 (x,y in [-1,1]);
+ *   prob_x [B,W,K] / prob_y [B,H,K] (get_coord's second return value; nullable);
+ *   maps [B,map_h,map_w,K] f32 (nullable: then only the soft-argmax runs).                        */
+int kp_softargmax_render_fwd(const float* logits, int B, int H, int W, int K,
+                             float* mu, float* prob_x, float* prob_y,
+                             float* maps, int map_h, int map_w, float inv_std, void* stream);
+
+/* Backward of the above.  d_maps [B,map_h,map_w,K] (nullable) and d_mu_extra [B,K,2] (nullable, a
+ * gradient arriving directly on mu) -> d_logits [B,H,W,K].  mu/prob_x/prob_y are the forward outputs.
+ * d_mu_scratch [B,K,2] is caller-owned scratch, only needed for shapes off the fast path (nullable
+ * for K=40, W=128).                                                                               */
+int kp_softargmax_render_bwd(const float* d_maps, const float* d_mu_extra,
+                             const float* mu, const float* prob_x, const float* prob_y,
+                             int B, int H, int W, int K, int map_h, int map_w, float inv_std,
+                             float* d_logits, float* d_mu_scratch, void* stream);
+
+/* get_gaussian_maps alone (utils/model.py:49-60; callers models/final_model.py:79-92,102-105,
+ * models/detector_translator_model.py:176-177).  mu [B,K,2] -> maps [B,h,w,K].                    */
+int kp_render_fwd(const float* mu, int B, int K, int h, int w, float inv_std, float* maps, void* stream);
+
+/* Its backward: d_maps [B,h,w,K] (+ optional d_mu_extra) -> d_mu [B,K,2].                          */
+int kp_render_bwd(const float* d_maps, const float* d_mu_extra, const float* mu,
+                  int B, int K, int h, int w, float inv_std, float* d_mu, void* stream);
+
+/* get_gaussian_maps + colorize_point_maps fused (utils/model.py:42-46 on :49-60; callers
+ * models/final_model.py:102-109, models/detector_translator_model.py:207-208).
+ * mu [B,K,2], colors [K,3] -> out [B,h,w,3].                                                       */
+int kp_render_colorize_fwd(const float* mu, const float* colors, int B, int K, int h, int w,
+                           float inv_std, float* out, void* stream);
+
+/* colorize_point_maps on already-materialised maps (utils/model.py:42-46).
+ * maps [n_pixels,K], colors [K,3] -> out [n_pixels,3] (max over k of maps*colour).                 */
+int kp_colorize_fwd(const float* maps, const float* colors, long long n_pixels, int K, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KP_B200_H */

@@ -1,0 +1,142 @@
+// Shared device/host helpers for the sm_100a kernels (mbarrier, TMA bulk copy, tcgen05).
+// Everything here is inline PTX for Blackwell; there is deliberately no fallback path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/kp_b200.h"
+
+#ifndef KP_SPIN_LIMIT
+#define KP_SPIN_LIMIT (1u << 26)   // bounded mbarrier spin: a lost arrival traps instead of hanging the GPU
+#endif
+
+namespace kp {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+// status codes: the KP_OK / KP_ERR_* macros of include/kp_b200.h
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define KP_CUDA_CHECK(expr)                                         \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return ::kp::cuda_fail(_e, #expr);   \
+    } while (0)
+
+// after every <<<>>>: check the launch and bump the library-wide launch counter (kp_launch_count()).
+void note_launch();
+#define KP_LAUNCHED()                                               \
+    do {                                                            \
+        KP_CUDA_CHECK(cudaGetLastError());                          \
+        ::kp::note_launch();                                        \
+    } while (0)
+
+#define KP_REQUIRE(cond, ...)                                       \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            ::kp::set_error(__VA_ARGS__);                           \
+            return KP_ERR_INVALID_ARG;                        \
+        }                                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: traps (-> CUDA error on the host) rather than hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > KP_SPIN_LIMIT) __trap();
+    }
+}
+
+// 1-D bulk async copy global -> shared, completion on an mbarrier (TMA engine, no tensor map).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// 1-D bulk async copy shared -> global (bulk-group completion).
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_shfl_xor(float4 v, int m) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                       __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+}  // namespace kp
