@@ -79,6 +79,63 @@ int kp_render_colorize_fwd(const float* mu, const float* colors, int B, int K, i
  * maps [n_pixels,K], colors [K,3] -> out [n_pixels,3] (max over k of maps*colour).                 */
 int kp_colorize_fwd(const float* maps, const float* colors, long long n_pixels, int K, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * C1/C2 — convolutions as tap-GEMMs on the tcgen05 tensor cores
+ *
+ * One primitive serves every convolution of the path (layers.conv, models/networks/layers.py:4-10, all
+ * call sites in models/networks/__init__.py:10-95,144-150; Vgg19.conv_layer, models/networks/vgg.py:48-55)
+ * forward AND data-gradient:
+ *
+ *     out[n,u,v, 0:Cout] = act( bias + sum_{tap t} sum_{source s} sum_c  A_{map(t)+s}[n, u+dh[t], v+dw[t], c] * Wp[:, k(t,s,c)] )
+ *
+ * where every A map is a strided 4-D view [N][Hd][Wd][C] of a bf16 NHWC tensor (out-of-range reads are
+ * zero = TF zero padding), Wp is a packed bf16 matrix [Cout_pad][Ktot] (K-major) and the output is a
+ * strided NHWC view (bf16 or f32).  Stride-2 convolutions use four parity views of the input (one per
+ * tap parity); stride-2 data-gradients use four launches with strided output views; channel concats are
+ * several sources per tap ("virtual concat", no copy).  The host mirror (kp_b200/conv.py) lowers TF
+ * SAME-padding convolutions onto this descriptor.
+ * Kernel: 128-pixel x BN-channel tiles, TMA (tile mode, hardware swizzle) into a multi-stage shared
+ * memory ring, tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM), fused epilogue.
+ * ------------------------------------------------------------------------------------------- */
+#define KP_MAX_MAPS 4
+#define KP_MAX_TAPS 64
+
+#define KP_ACT_NONE 0
+#define KP_ACT_RELU 1
+#define KP_ACT_LEAKY 2      /* x >= 0 ? x : alpha*x */
+#define KP_ACT_SIGMOID 3
+#define KP_ACT_SIGMOID_LAST 4 /* channels [0,Cout-1) linear, channel Cout-1 sigmoid (translator heads) */
+
+typedef struct {
+    int src;               /* which of the src[] pointers this view reads */
+    int C;                 /* channels (multiple of 8) */
+    int Wd, Hd;            /* view extent; reads outside [0,Wd) x [0,Hd) x [0,N) return 0 */
+    long long off;         /* element offset of view(0,0,0,0) from the source pointer */
+    long long sw, sh, sn;  /* element strides of the view (multiples of 8) */
+} kp_tap_view;
+
+typedef struct {
+    int N;                                   /* images */
+    int n_maps;  kp_tap_view map[KP_MAX_MAPS];
+    int n_taps, n_src;                       /* each tap reads n_src consecutive maps starting at map_first[t] */
+    signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], map_first[KP_MAX_TAPS];
+    int CB;                                  /* channel block: 16, 32 or 64 (= swizzle span 32/64/128 B) */
+    int Cout_pad, Ktot;                      /* packed weight matrix [Cout_pad][Ktot] bf16 */
+    int Ho, Wo;                              /* output extent in tile space */
+    long long out_off, out_sw, out_sh, out_sn; /* output view (elements) */
+    int Cout;                                /* channels written per pixel */
+    int out_f32;                             /* 0: bf16 output, 1: f32 output */
+    int act; float alpha;
+    int TW, TH, TN, BN;                      /* tile: TW*TH*TN == 128 pixels x BN channels; 0 = let the library choose */
+} kp_tapconv_desc;
+
+/* src[i]: bf16 NHWC sources; wpacked: bf16 [Cout_pad][Ktot]; bias: f32 [Cout_pad] (nullable);
+ * out: bf16 or f32 view; stats_sum / stats_sq: f32 [Cout_pad] accumulators (nullable) that receive
+ * per-channel sum and sum of squares of the PRE-bias accumulators (for batch-norm statistics,
+ * models/networks/layers.py:13-14) via atomic adds.                                                */
+int kp_tapconv_bf16(const kp_tapconv_desc* desc, const void* const* src, const void* wpacked, const float* bias,
+                    void* out, float* stats_sum, float* stats_sq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

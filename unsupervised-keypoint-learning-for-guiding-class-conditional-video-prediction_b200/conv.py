@@ -1,0 +1,88 @@
+"""Torch-facing wrappers of the tap-GEMM convolution primitive (kp_tapconv_bf16).
+
+PyTorch is plumbing: it owns the buffers and the stream and does the (pure data-movement) weight
+re-layout; all arithmetic of the convolution runs in csrc/conv_tc.cu on the tcgen05 tensor cores.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import tapconv as tc
+from .tapconv import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIGMOID_LAST  # noqa: F401
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pack_weights(plan, w, row_scale=None, dtype=torch.bfloat16):
+    """HWIO float kernel [k,k,Cin,Cout] -> packed [rows_pad, Ktot] bf16 (K-major) following plan.pack.
+
+    `row_scale` (fwd mode, [Cout]) multiplies each output channel's weights (batch-norm folding).
+    Mirrors tapconv.pack_weights_np (which the CPU tests pin against the conv oracle).
+    """
+    k1, k2, cin, cout = w.shape
+    CB = plan.CB
+    taps = torch.as_tensor(plan.pack["taps"], device=w.device, dtype=torch.long)
+    w3 = w.reshape(k1 * k2, cin, cout).index_select(0, taps)
+    if plan.pack["mode"] == "fwd":
+        if row_scale is not None:
+            w3 = w3 * row_scale.view(1, 1, cout)
+        parts = []
+        for c_start, c_count in plan.pack["segs"]:
+            seg = w3[:, c_start:c_start + c_count, :]
+            padc = tc.round_up(c_count, CB) - c_count
+            if padc:
+                seg = torch.nn.functional.pad(seg, (0, 0, 0, padc))
+            parts.append(seg)
+        wk = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        m = wk.permute(2, 0, 1).reshape(cout, -1)
+    else:
+        c0, c1 = plan.pack["row_slice"]
+        seg = w3[:, c0:c1, :]
+        padc = tc.round_up(cout, CB) - cout
+        if padc:
+            seg = torch.nn.functional.pad(seg, (0, padc))
+        m = seg.permute(1, 0, 2).reshape(c1 - c0, -1)
+    if m.shape[0] != plan.rows_pad:
+        m = torch.nn.functional.pad(m, (0, 0, 0, plan.rows_pad - m.shape[0]))
+    assert m.shape == (plan.rows_pad, plan.Ktot), (tuple(m.shape), plan.rows_pad, plan.Ktot)
+    return m.to(dtype).contiguous()
+
+
+def pad_vec(v, n):
+    """f32 vector padded with zeros to length n (bias / statistics buffers are [Cout_pad])."""
+    v = v.to(torch.float32)
+    if v.shape[0] == n:
+        return v.contiguous()
+    return torch.nn.functional.pad(v, (0, n - v.shape[0])).contiguous()
+
+
+def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None, cout_written=None, tile=None, bn=0):
+    """Launch one tap-GEMM.  srcs: bf16 NHWC CUDA tensors; out: bf16 or f32 tensor written through the plan's
+    output view; bias: f32 [rows_pad] or None; stats: (sum, sumsq) f32 [rows_pad] accumulators or None."""
+    for s in srcs:
+        if not (s.is_cuda and s.dtype == torch.bfloat16 and s.is_contiguous()):
+            raise ValueError("tap-GEMM sources must be contiguous bf16 CUDA tensors")
+    if not (wpacked.is_cuda and wpacked.dtype == torch.bfloat16 and wpacked.is_contiguous()
+            and tuple(wpacked.shape) == (plan.rows_pad, plan.Ktot)):
+        raise ValueError("packed weights must be bf16 [rows_pad=%d, Ktot=%d]" % (plan.rows_pad, plan.Ktot))
+    if out.dtype not in (torch.bfloat16, torch.float32) or not out.is_cuda:
+        raise ValueError("output must be a bf16 or f32 CUDA tensor")
+    if bias is not None and (bias.dtype != torch.float32 or bias.shape[0] != plan.rows_pad):
+        raise ValueError("bias must be f32 [rows_pad]")
+    d = plan.desc(act=act, alpha=alpha, out_f32=(out.dtype == torch.float32), cout_written=cout_written, tile=tile, bn=bn)
+    ptrs = (ctypes.c_void_p * tc.KP_MAX_MAPS)()
+    for i, s in enumerate(srcs):
+        ptrs[i] = s.data_ptr()
+    ssum = ssq = None
+    if stats is not None:
+        ssum, ssq = stats
+        if ssum.dtype != torch.float32 or ssum.shape[0] != plan.rows_pad or ssq.shape[0] != plan.rows_pad:
+            raise ValueError("stats buffers must be f32 [rows_pad]")
+    with torch.cuda.device(out.device):
+        _lib.call("kp_tapconv_bf16", ctypes.byref(d), ptrs, wpacked.data_ptr(),
+                  None if bias is None else bias.data_ptr(), out.data_ptr(),
+                  None if ssum is None else ssum.data_ptr(), None if ssq is None else ssq.data_ptr(), _stream())
+    return out

@@ -1,0 +1,405 @@
+// Tap-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Serves every convolution of the stage-1 path (reference: layers.conv, models/networks/layers.py:4-10;
+// Vgg19.conv_layer, models/networks/vgg.py:48-55), forward and data-gradient; see include/kp_b200.h.
+//
+// Per CTA: one 128-pixel x BN-channel output tile.
+//   warp 0     TMA producer  - per K step one 4-D box [TN][TH][TW][CB] of the (shifted) activation view
+//                              (zero fill outside the image = TF zero padding) + one 2-D box [BN][CB] of
+//                              the packed weights, both hardware-swizzled, into an S-stage smem ring;
+//   warp 1     MMA issuer    - tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16, fp32 accumulators
+//                              in TMEM; tcgen05.commit releases ring slots / signals the epilogue;
+//   warps 2-5  epilogue      - tcgen05.ld 32x32b (one output pixel per thread), optional per-channel
+//                              sum / sum-of-squares (batch-norm statistics) by a warp transpose-reduce +
+//                              atomics, bias + activation, bf16/f32 NHWC stores.
+#include "kp_tc.cuh"
+#include "kp_internal.h"
+#include <cudaTypedefs.h>
+#include <string.h>
+
+namespace kp {
+
+struct alignas(64) TapConvKParams {
+    CUtensorMap mapA[KP_MAX_MAPS];
+    CUtensorMap mapB;
+    int n_taps, n_src;
+    int nblk[KP_MAX_MAPS];
+    signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], mf[KP_MAX_TAPS];
+    int TW, TH, TN, tiles_w, tiles_h;
+    int Ho, Wo, N;
+    int BN, tmem_cols, stages, total_iters;
+    uint32_t a_bytes, b_bytes, stage_bytes;
+    void* out;
+    long long out_off, out_sw, out_sh, out_sn;
+    int Cout, out_f32, act;
+    float alpha;
+    const float* bias;
+    float* ssum;
+    float* ssq;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act, float alpha, bool last) {
+    switch (act) {
+        case KP_ACT_RELU: return fmaxf(x, 0.f);
+        case KP_ACT_LEAKY: return x >= 0.f ? x : alpha * x;
+        case KP_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+        case KP_ACT_SIGMOID_LAST: return last ? 1.f / (1.f + __expf(-x)) : x;
+        default: return x;
+    }
+}
+
+// 32 lanes x 16 columns -> per-column totals: lane l ends with the total of column
+// (bit4*8 + bit3*4 + bit2*2 + bit1) of l; 16 shuffles instead of 80.
+__device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
+    float a[8];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float keep = up ? v[j + 8] : v[j], send = up ? v[j] : v[j + 8];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    float b[4];
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float keep = up ? a[j + 4] : a[j], send = up ? a[j] : a[j + 4];
+            b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    float c[2];
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float keep = up ? b[j + 2] : b[j], send = up ? b[j] : b[j + 2];
+            c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    float d;
+    {
+        const bool up = lane & 2;
+        const float keep = up ? c[1] : c[0], send = up ? c[0] : c[1];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+template <int CB>
+__global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__ TapConvKParams p) {
+    constexpr uint32_t ROW_BYTES = CB * 2;
+    constexpr uint32_t SBO = 8 * ROW_BYTES;
+    constexpr uint32_t LAYOUT = (CB == 64) ? 2u : (CB == 32) ? 4u : 6u;
+
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* base = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)p.stages * p.stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+
+    const int mt = blockIdx.x;
+    const int tw_i = mt % p.tiles_w, th_i = (mt / p.tiles_w) % p.tiles_h, tn_i = mt / (p.tiles_w * p.tiles_h);
+    const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+    const int n_off = blockIdx.y * p.BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int m = 0; m < KP_MAX_MAPS; ++m)
+                if (p.nblk[m] > 0) tma_prefetch_desc(&p.mapA[m]);
+            tma_prefetch_desc(&p.mapB);
+            int it = 0;
+            for (int t = 0; t < p.n_taps; ++t) {
+                const int cw = w0 + p.dw[t], ch = h0 + p.dh[t];
+                for (int s = 0; s < p.n_src; ++s) {
+                    const int m = p.mf[t] + s;
+                    const int nb = p.nblk[m];
+                    for (int cb = 0; cb < nb; ++cb, ++it) {
+                        const int st = it % S;
+                        if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
+                        uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
+                        mbar_arrive_expect_tx(&full[st], p.a_bytes + p.b_bytes);
+                        tma_load_4d(a_dst, &p.mapA[m], &full[st], cb * CB, cw, ch, n0);
+                        tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it * CB, n_off);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+            for (int it = 0; it < p.total_iters; ++it) {
+                const int st = it % S;
+                mbar_wait(&full[st], (it / S) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + (uint32_t)st * p.stage_bytes;
+                const uint32_t b_addr = a_addr + p.a_bytes;
+#pragma unroll
+                for (int k = 0; k < CB / 16; ++k) {
+                    const uint64_t da = umma_smem_desc(a_addr + k * 32, SBO, 16, LAYOUT);
+                    const uint64_t db = umma_smem_desc(b_addr + k * 32, SBO, 16, LAYOUT);
+                    umma_bf16(tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[st]);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        // ------------------------------- epilogue -------------------------------
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+        const int uw = w0 + tw, uh = h0 + th, n = n0 + tn;
+        const bool valid = (uw < p.Wo) && (uh < p.Ho) && (n < p.N);
+        const long long pix = p.out_off + (long long)n * p.out_sn + (long long)uh * p.out_sh + (long long)uw * p.out_sw;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            float v[16];
+            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-pixel predicated stores
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int ch0 = n_off + c0;
+            if (p.ssum != nullptr) {
+                float sq[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                const float s1 = warp_colsum16(v, lane);
+                const float s2 = warp_colsum16(sq, lane);
+                if ((lane & 1) == 0) {
+                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    atomicAdd(p.ssum + ch0 + col, s1);
+                    atomicAdd(p.ssq + ch0 + col, s2);
+                }
+            }
+            if (valid && ch0 < p.Cout) {
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + ch0 + j);
+            }
+            if (p.act != KP_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act, p.alpha, ch0 + j == p.Cout - 1);
+            }
+            const int nvalid = min(16, p.Cout - ch0);
+            if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
+                if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    for (int j = 0; j < nvalid; ++j) o[j] = v[j];
+                }
+            } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + ch0;
+                if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    uint4* o4 = reinterpret_cast<uint4*>(o);
+                    o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                } else {
+                    for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(v[j]);
+                }
+            }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable (cuda error %d, query %d)", (int)e, (int)qres);
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int CB) {
+    return CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static int pow2_at_least(int v, int lo) {
+    int r = lo;
+    while (r < v) r <<= 1;
+    return r;
+}
+
+// pick TW,TH,TN (product 128, powers of two) minimising padded pixels
+static void choose_tile(int Wo, int Ho, int N, int* TW, int* TH, int* TN) {
+    long long best = -1;
+    for (int tw = 1; tw <= 128; tw <<= 1) {
+        for (int th = 1; tw * th <= 128; th <<= 1) {
+            const int tn = 128 / (tw * th);
+            const long long cover = (long long)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th *
+                                    ((N + tn - 1) / tn) * tn;
+            // prefer wide tiles on ties (longer contiguous runs for TMA and for the stores)
+            if (best < 0 || cover < best || (cover == best && tw > *TW)) {
+                best = cover;
+                *TW = tw; *TH = th; *TN = tn;
+            }
+        }
+    }
+}
+
+int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
+                   float* ssum, float* ssq, cudaStream_t st) {
+    KP_REQUIRE(d->CB == 16 || d->CB == 32 || d->CB == 64, "kp_tapconv: CB must be 16, 32 or 64 (got %d)", d->CB);
+    KP_REQUIRE(d->n_maps >= 1 && d->n_maps <= KP_MAX_MAPS, "kp_tapconv: n_maps %d out of range", d->n_maps);
+    KP_REQUIRE(d->n_taps >= 1 && d->n_taps <= KP_MAX_TAPS, "kp_tapconv: n_taps %d out of range", d->n_taps);
+    KP_REQUIRE(d->n_src >= 1 && d->n_src <= KP_MAX_MAPS, "kp_tapconv: n_src %d out of range", d->n_src);
+    KP_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cout > 0, "kp_tapconv: empty problem");
+    KP_REQUIRE((ssum == nullptr) == (ssq == nullptr), "kp_tapconv: stats_sum and stats_sq go together");
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) return KP_ERR_DRIVER;
+
+    TapConvKParams p;
+    memset(&p, 0, sizeof(p));
+    const int CB = d->CB;
+    int TW = d->TW, TH = d->TH, TN = d->TN, BN = d->BN;
+    if (TW <= 0 || TH <= 0 || TN <= 0) choose_tile(d->Wo, d->Ho, d->N, &TW, &TH, &TN);
+    KP_REQUIRE(TW * TH * TN == 128, "kp_tapconv: tile %dx%dx%d is not 128 pixels", TW, TH, TN);
+    if (BN <= 0) {
+        BN = d->Cout_pad <= 256 ? d->Cout_pad : (d->Cout_pad % 256 == 0 ? 256 : 128);
+    }
+    KP_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && d->Cout_pad % BN == 0,
+               "kp_tapconv: BN=%d must be a multiple of 16 in [16,256] dividing Cout_pad=%d", BN, d->Cout_pad);
+    KP_REQUIRE(d->Cout <= d->Cout_pad, "kp_tapconv: Cout > Cout_pad");
+
+    // A maps
+    int total_blocks_per_tap = -1;
+    for (int m = 0; m < d->n_maps; ++m) {
+        const kp_tap_view& v = d->map[m];
+        KP_REQUIRE(v.C > 0 && v.C % 8 == 0, "kp_tapconv: map %d channels %d must be a positive multiple of 8", m, v.C);
+        KP_REQUIRE(v.sw % 8 == 0 && v.sh % 8 == 0 && v.sn % 8 == 0 && v.off % 8 == 0,
+                   "kp_tapconv: map %d strides/offset must be multiples of 8 elements (16 B)", m);
+        KP_REQUIRE(v.src >= 0 && v.src < KP_MAX_MAPS && src[v.src] != nullptr, "kp_tapconv: map %d has no source", m);
+        const char* basep = reinterpret_cast<const char*>(src[v.src]) + v.off * 2;
+        KP_REQUIRE((reinterpret_cast<uintptr_t>(basep) & 15) == 0, "kp_tapconv: map %d base not 16-byte aligned", m);
+        cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.Wd, (cuuint64_t)v.Hd, (cuuint64_t)d->N};
+        cuuint64_t gstr[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+        cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&p.mapA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(basep), gdim, gstr, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("kp_tapconv: cuTensorMapEncodeTiled(A map %d) failed with %d (C=%d W=%d H=%d N=%d)", m, (int)r, v.C,
+                      v.Wd, v.Hd, d->N);
+            return KP_ERR_DRIVER;
+        }
+        p.nblk[m] = (v.C + CB - 1) / CB;
+    }
+    int total_iters = 0;
+    for (int t = 0; t < d->n_taps; ++t) {
+        KP_REQUIRE(d->map_first[t] >= 0 && d->map_first[t] + d->n_src <= d->n_maps, "kp_tapconv: tap %d maps out of range", t);
+        int blocks = 0;
+        for (int s = 0; s < d->n_src; ++s) blocks += p.nblk[d->map_first[t] + s];
+        if (total_blocks_per_tap < 0) total_blocks_per_tap = blocks;
+        KP_REQUIRE(blocks == total_blocks_per_tap, "kp_tapconv: taps must read the same number of channel blocks");
+        total_iters += blocks;
+        p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.mf[t] = d->map_first[t];
+    }
+    KP_REQUIRE(d->Ktot == total_iters * CB, "kp_tapconv: Ktot=%d does not match taps x blocks x CB = %d", d->Ktot,
+               total_iters * CB);
+    {
+        KP_REQUIRE((reinterpret_cast<uintptr_t>(wpacked) & 15) == 0, "kp_tapconv: packed weights not 16-byte aligned");
+        cuuint64_t gdim[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Cout_pad};
+        cuuint64_t gstr[1] = {(cuuint64_t)d->Ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)CB, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("kp_tapconv: cuTensorMapEncodeTiled(weights) failed with %d (Ktot=%d Cout_pad=%d)", (int)r, d->Ktot,
+                      d->Cout_pad);
+            return KP_ERR_DRIVER;
+        }
+    }
+    p.n_taps = d->n_taps; p.n_src = d->n_src;
+    p.TW = TW; p.TH = TH; p.TN = TN;
+    p.tiles_w = (d->Wo + TW - 1) / TW;
+    p.tiles_h = (d->Ho + TH - 1) / TH;
+    const int tiles_n = (d->N + TN - 1) / TN;
+    p.Ho = d->Ho; p.Wo = d->Wo; p.N = d->N;
+    p.BN = BN;
+    p.tmem_cols = pow2_at_least(BN, 32);
+    p.total_iters = total_iters;
+    p.a_bytes = 128u * CB * 2u;
+    p.b_bytes = (uint32_t)BN * CB * 2u;
+    p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+    int stages = (int)((200u * 1024u) / p.stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages > total_iters) stages = total_iters;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    p.out = out;
+    p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
+    p.Cout = d->Cout; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha;
+    p.bias = bias; p.ssum = ssum; p.ssq = ssq;
+
+    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)(d->Cout_pad / BN), 1);
+    KP_REQUIRE(grid.y <= 65535, "kp_tapconv: too many channel tiles");
+#define KP_LAUNCH_TAPCONV(CBV)                                                                                      \
+    do {                                                                                                            \
+        static bool attr_done = false;                                                                              \
+        if (!attr_done) {                                                                                           \
+            KP_CUDA_CHECK(cudaFuncSetAttribute(tapconv_kernel<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                               227 * 1024));                                                        \
+            attr_done = true;                                                                                       \
+        }                                                                                                           \
+        tapconv_kernel<CBV><<<grid, 192, smem, st>>>(p);                                                            \
+    } while (0)
+    if (CB == 64) KP_LAUNCH_TAPCONV(64);
+    else if (CB == 32) KP_LAUNCH_TAPCONV(32);
+    else KP_LAUNCH_TAPCONV(16);
+#undef KP_LAUNCH_TAPCONV
+    KP_LAUNCHED();
+    return KP_OK;
+}
+
+}  // namespace kp

@@ -98,4 +98,10 @@ int kp_colorize_fwd(const float* maps, const float* colors, long long n_pixels, 
     return k1_colorize(maps, colors, n_pixels, K, out, static_cast<cudaStream_t>(stream));
 }
 
+int kp_tapconv_bf16(const kp_tapconv_desc* desc, const void* const* src, const void* wpacked, const float* bias,
+                    void* out, float* stats_sum, float* stats_sq, void* stream) {
+    KP_NONNULL(desc); KP_NONNULL(src); KP_NONNULL(wpacked); KP_NONNULL(out);
+    return tapconv_launch(desc, src, wpacked, bias, out, stats_sum, stats_sq, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

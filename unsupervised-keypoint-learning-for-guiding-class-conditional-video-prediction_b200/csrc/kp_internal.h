@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/kp_b200.h"
 
 namespace kp {
 
@@ -17,5 +18,9 @@ int k1_render_bwd(const float* d_maps, const float* d_mu_extra, const float* mu,
 int k1_render_colorize(const float* mu, const float* colors, int B, int K, int hm, int wm, float inv_std, float* out,
                        cudaStream_t st);
 int k1_colorize(const float* maps, const float* colors, long long P, int K, float* out, cudaStream_t st);
+
+// conv_tc.cu
+int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
+                   float* ssum, float* ssq, cudaStream_t st);
 
 }  // namespace kp

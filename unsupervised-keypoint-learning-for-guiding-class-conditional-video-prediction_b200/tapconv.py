@@ -1,0 +1,236 @@
+"""Host-side lowering of TF-style convolutions onto the tap-GEMM primitive (kp_tapconv_bf16).
+
+Pure geometry — no torch, no CUDA — so that it can be unit-tested on a CPU box against the oracle
+(tests/test_tapconv_lowering.py runs these plans through a numpy emulator of the device primitive).
+
+Reference semantics being lowered: layers.conv (/root/reference/models/networks/layers.py:4-10) =
+tf.pad(pad) + tf.layers.conv2d(padding='same', strides=s); its data-gradient; channel concats feeding a
+convolution (models/networks/__init__.py:44) as several sources per tap.
+"""
+import ctypes
+
+import numpy as np
+
+KP_MAX_MAPS = 4
+KP_MAX_TAPS = 64
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_SIGMOID_LAST = 0, 1, 2, 3, 4
+
+
+class TapView(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_int), ("C", ctypes.c_int), ("Wd", ctypes.c_int), ("Hd", ctypes.c_int),
+                ("off", ctypes.c_longlong), ("sw", ctypes.c_longlong), ("sh", ctypes.c_longlong),
+                ("sn", ctypes.c_longlong)]
+
+
+class TapConvDesc(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("n_maps", ctypes.c_int), ("map", TapView * KP_MAX_MAPS),
+                ("n_taps", ctypes.c_int), ("n_src", ctypes.c_int),
+                ("dh", ctypes.c_byte * KP_MAX_TAPS), ("dw", ctypes.c_byte * KP_MAX_TAPS),
+                ("map_first", ctypes.c_byte * KP_MAX_TAPS),
+                ("CB", ctypes.c_int), ("Cout_pad", ctypes.c_int), ("Ktot", ctypes.c_int),
+                ("Ho", ctypes.c_int), ("Wo", ctypes.c_int),
+                ("out_off", ctypes.c_longlong), ("out_sw", ctypes.c_longlong), ("out_sh", ctypes.c_longlong),
+                ("out_sn", ctypes.c_longlong),
+                ("Cout", ctypes.c_int), ("out_f32", ctypes.c_int), ("act", ctypes.c_int), ("alpha", ctypes.c_float),
+                ("TW", ctypes.c_int), ("TH", ctypes.c_int), ("TN", ctypes.c_int), ("BN", ctypes.c_int)]
+
+
+def same_pad(in_size, k, s):
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return total // 2, total - total // 2
+
+
+def round_up(v, m):
+    return -(-v // m) * m
+
+
+def pick_cb(channels):
+    for cb in (64, 32):
+        if all(c % cb == 0 for c in channels):
+            return cb
+    return 16
+
+
+class TapPlan:
+    """One launch of the device primitive: views, taps, weight gather index, output view."""
+
+    def __init__(self):
+        self.N = 0
+        self.views = []        # dicts: src, C, Wd, Hd, off, sw, sh, sn
+        self.n_src = 1
+        self.taps = []         # (dh, dw, map_first)
+        self.CB = 16
+        self.rows = 0          # real rows of the packed matrix (output channels of this GEMM)
+        self.rows_pad = 0
+        self.Ktot = 0
+        self.Ho = self.Wo = 0  # tile-space output extent
+        self.out_off = 0
+        self.out_sw = self.out_sh = self.out_sn = 0
+        self.pack = None       # weight packing recipe (mode, taps, segs, row_slice)
+
+    def blocks_per_tap(self):
+        first = self.taps[0][2]
+        return sum(-(-self.views[first + s]["C"] // self.CB) for s in range(self.n_src))
+
+    def desc(self, act=ACT_NONE, alpha=0.0, out_f32=False, cout_written=None, tile=None, bn=0):
+        d = TapConvDesc()
+        d.N = self.N
+        d.n_maps = len(self.views)
+        for i, v in enumerate(self.views):
+            d.map[i].src, d.map[i].C, d.map[i].Wd, d.map[i].Hd = v["src"], v["C"], v["Wd"], v["Hd"]
+            d.map[i].off, d.map[i].sw, d.map[i].sh, d.map[i].sn = v["off"], v["sw"], v["sh"], v["sn"]
+        d.n_taps = len(self.taps)
+        d.n_src = self.n_src
+        for i, (dh, dw, mf) in enumerate(self.taps):
+            d.dh[i], d.dw[i], d.map_first[i] = dh, dw, mf
+        d.CB, d.Cout_pad, d.Ktot = self.CB, self.rows_pad, self.Ktot
+        d.Ho, d.Wo = self.Ho, self.Wo
+        d.out_off, d.out_sw, d.out_sh, d.out_sn = self.out_off, self.out_sw, self.out_sh, self.out_sn
+        d.Cout = self.rows if cout_written is None else cout_written
+        d.out_f32 = 1 if out_f32 else 0
+        d.act, d.alpha = act, alpha
+        if tile is not None:
+            d.TW, d.TH, d.TN = tile
+        d.BN = bn
+        return d
+
+
+def _finish(plan, rows, mode, tap_flat, segs, row_slice=None):
+    """Record the weight-packing recipe (see pack_weights_np / ops.pack_weights)."""
+    CB = plan.CB
+    plan.rows = rows
+    plan.rows_pad = round_up(rows, 16)
+    per_tap = sum(round_up(c, CB) for _, c in segs)
+    plan.Ktot = per_tap * len(plan.taps)
+    plan.pack = dict(mode=mode, taps=list(tap_flat), segs=list(segs), row_slice=row_slice)
+    return plan
+
+
+def pack_weights_np(plan, w):
+    """numpy twin of the device-side weight packing: HWIO kernel -> [rows_pad, Ktot] (K-major)."""
+    k1, k2, cin, cout = w.shape
+    w3 = w.reshape(k1 * k2, cin, cout)[plan.pack["taps"]]            # [T, cin, cout]
+    CB = plan.CB
+    if plan.pack["mode"] == "fwd":
+        parts = []
+        for c_start, c_count in plan.pack["segs"]:
+            seg = w3[:, c_start:c_start + c_count, :]
+            padc = round_up(c_count, CB) - c_count
+            parts.append(np.pad(seg, ((0, 0), (0, padc), (0, 0))))
+        wk = np.concatenate(parts, axis=1)                              # [T, Kper, cout]
+        m = np.transpose(wk, (2, 0, 1)).reshape(cout, -1)
+    else:
+        c0, c1 = plan.pack["row_slice"]
+        seg = w3[:, c0:c1, :]                                           # [T, rows, cout]
+        padc = round_up(cout, CB) - cout
+        seg = np.pad(seg, ((0, 0), (0, 0), (0, padc)))
+        m = np.transpose(seg, (1, 0, 2)).reshape(c1 - c0, -1)
+    out = np.zeros((plan.rows_pad, plan.Ktot), dtype=w.dtype)
+    out[:m.shape[0]] = m
+    return out
+
+
+def plan_conv_fwd(src_shapes, k, stride, pad, cout, out_channels_total=None, out_channel_off=0):
+    """Forward convolution of the channel-concat of `src_shapes` [(N,H,W,C), ...] with an HWIO kernel
+    [k,k,sum(C),cout].  Output tensor is NHWC with `out_channels_total` channels (default cout); this conv
+    writes channels [out_channel_off, out_channel_off+cout).  Returns (plan, (N,Ho,Wo))."""
+    N, H, W, _ = src_shapes[0]
+    for s in src_shapes:
+        assert s[:3] == (N, H, W), "concat sources must share N,H,W"
+    Cs = [s[3] for s in src_shapes]
+    cin = sum(Cs)
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    Ho, Wo = -(-Hp // stride), -(-Wp // stride)
+    pt = pad + same_pad(Hp, k, stride)[0]
+    pl = pad + same_pad(Wp, k, stride)[0]
+    p = TapPlan()
+    p.N = N
+    p.CB = pick_cb(Cs)
+    p.n_src = len(Cs)
+    tap_k = []
+    if stride == 1:
+        for i, C in enumerate(Cs):
+            p.views.append(dict(src=i, C=C, Wd=W, Hd=H, off=0, sw=C, sh=W * C, sn=H * W * C))
+        for kh in range(k):
+            for kw in range(k):
+                p.taps.append((kh - pt, kw - pl, 0))
+                tap_k.append((kh, kw))
+    elif stride == 2:
+        assert len(Cs) == 1, "stride-2 convolutions take a single source on this path"
+        C = Cs[0]
+        used = {}
+        for kh in range(k):
+            for kw in range(k):
+                eh, ew = kh - pt, kw - pl
+                ph, pw = eh % 2, ew % 2
+                key = (ph, pw)
+                if key not in used:
+                    used[key] = len(p.views)
+                    p.views.append(dict(src=0, C=C, Wd=-(-(W - pw) // 2), Hd=-(-(H - ph) // 2), off=(ph * W + pw) * C,
+                                        sw=2 * C, sh=2 * W * C, sn=H * W * C))
+                p.taps.append(((eh - ph) // 2, (ew - pw) // 2, used[key]))
+                tap_k.append((kh, kw))
+    else:
+        raise ValueError("stride must be 1 or 2")
+    assert len(p.taps) <= KP_MAX_TAPS and len(p.views) <= KP_MAX_MAPS
+    ct = cout if out_channels_total is None else out_channels_total
+    p.Ho, p.Wo = Ho, Wo
+    p.out_off, p.out_sw, p.out_sh, p.out_sn = out_channel_off, ct, Wo * ct, Ho * Wo * ct
+
+    segs, base = [], 0
+    for C in Cs:
+        segs.append((base, C))
+        base += C
+    _finish(p, cout, "fwd", [kh * k + kw for kh, kw in tap_k], segs)
+    return p, (N, Ho, Wo)
+
+
+def plan_conv_dgrad(x_shape, k, stride, pad, cout, cin_slice=None):
+    """Data gradient of plan_conv_fwd: dY [N,Ho,Wo,cout] -> dX [N,H,W,Cin] (Cin = x_shape[3]).
+
+    `cin_slice=(c0, c1, cin_total)`: produce only input channels [c0,c1) of a kernel with cin_total input
+    channels (gradient w.r.t. ONE source of a virtual concat).  Returns a list of plans (1 for stride 1,
+    up to 4 parity classes for stride 2); each writes a strided view of dX.
+    """
+    N, H, W, Cx = x_shape
+    c0, c1, cin_total = (0, Cx, Cx) if cin_slice is None else cin_slice
+    assert c1 - c0 == Cx
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    Ho, Wo = -(-Hp // stride), -(-Wp // stride)
+    pt = pad + same_pad(Hp, k, stride)[0]
+    pl = pad + same_pad(Wp, k, stride)[0]
+    plans = []
+    classes = [(0, 0)] if stride == 1 else [(0, 0), (0, 1), (1, 0), (1, 1)]
+    for ah, aw in classes:
+        p = TapPlan()
+        p.N = N
+        p.CB = pick_cb([cout])
+        p.n_src = 1
+        p.views.append(dict(src=0, C=cout, Wd=Wo, Hd=Ho, off=0, sw=cout, sh=Wo * cout, sn=Ho * Wo * cout))
+        tap_k = []
+        for kh in range(k):
+            for kw in range(k):
+                if stride == 1:
+                    p.taps.append((pt - kh, pl - kw, 0))
+                    tap_k.append((kh, kw))
+                else:
+                    if (ah - kh + pt) % 2 or (aw - kw + pl) % 2:
+                        continue
+                    p.taps.append(((ah - kh + pt) // 2, (aw - kw + pl) // 2, 0))
+                    tap_k.append((kh, kw))
+        if not p.taps:
+            continue
+        if stride == 1:
+            p.Ho, p.Wo = H, W
+            p.out_off, p.out_sw, p.out_sh, p.out_sn = 0, Cx, W * Cx, H * W * Cx
+        else:
+            p.Ho, p.Wo = -(-(H - ah) // 2), -(-(W - aw) // 2)
+            if p.Ho <= 0 or p.Wo <= 0:
+                continue
+            p.out_off, p.out_sw, p.out_sh, p.out_sn = (ah * W + aw) * Cx, 2 * Cx, 2 * W * Cx, H * W * Cx
+
+        _finish(p, Cx, "dgrad", [kh * k + kw for kh, kw in tap_k], [(0, cout)], row_slice=(c0, c1))
+        plans.append(p)
+    return plans
