@@ -136,6 +136,30 @@ typedef struct {
 int kp_tapconv_bf16(const kp_tapconv_desc* desc, const void* const* src, const void* wpacked, const float* bias,
                     void* out, float* stats_sum, float* stats_sq, void* stream);
 
+/* Weight gradient of the same convolutions (the backward of layers.conv w.r.t. its kernel):
+ *
+ *     dW[tap t][ci][co] += sum_{n,u,v}  X_{map(t)}[n, u+dh[t], v+dw[t], ci] * dY[n,u,v,co]
+ *
+ * Both operands are read with the SAME 4-D TMA boxes as the forward pass ([pixels][channels], channels
+ * contiguous) and fed to tcgen05.mma as MN-major matrices (M = ci, N = co, K = pixels), so no transposed
+ * copy of the activations is ever made.  grid = (ci blocks x co blocks, taps, pixel splits); partial sums
+ * are accumulated into the f32 HWIO gradient with atomic adds (the caller zeroes dW first).            */
+typedef struct {
+    int N;
+    int n_maps;  kp_tap_view map[KP_MAX_MAPS];   /* X views (one per tap parity for stride 2) */
+    kp_tap_view dy;                               /* dY view [N][Ho][Wo][Cout] */
+    int n_taps;
+    signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], map_first[KP_MAX_TAPS];
+    int tap_flat[KP_MAX_TAPS];                   /* kh*k+kw of each tap (row of the HWIO kernel) */
+    int CB;                                      /* channel block 16/32/64 (both operands) */
+    int Ho, Wo;                                  /* pixel iteration space (= dY extent) */
+    int Cin, Cout;                               /* rows / columns written */
+    long long dw_off, dw_stap, dw_sci;           /* dW element (t,ci,co) at dw_off + tap_flat[t]*dw_stap + ci*dw_sci + co */
+    int splits;                                  /* pixel-range splits (grid.z); 0 = library chooses */
+} kp_wgrad_desc;
+
+int kp_tapconv_wgrad_bf16(const kp_wgrad_desc* desc, const void* x, const void* dy, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

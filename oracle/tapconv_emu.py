@@ -55,3 +55,31 @@ def run_plan(plan, srcs, wpacked, bias, out, act=None):
     obase = plan.out_off + n_idx * plan.out_sn + h_idx * plan.out_sh + w_idx * plan.out_sw
     oflat[obase[..., None] + np.arange(plan.rows)[None, None, None, :]] = Y
     return out
+
+
+def run_wgrad_plan(plan, x, dy, dw):
+    """Emulates kp_tapconv_wgrad_bf16: dw (flattened HWIO, f64) += sum_pixels X_tap^T dY."""
+    xf = np.ascontiguousarray(x).reshape(-1)
+    dyf = np.ascontiguousarray(dy).reshape(-1)
+    dwf = dw.reshape(-1)
+    N, Ho, Wo = plan.N, plan.Ho, plan.Wo
+
+    def gather(flat, v, dh, dw_):
+        C = v["C"]
+        hh = np.arange(Ho) + dh
+        ww = np.arange(Wo) + dw_
+        ok = ((hh >= 0) & (hh < v["Hd"]))[None, :, None] & ((ww >= 0) & (ww < v["Wd"]))[None, None, :] \
+            & np.ones((N, 1, 1), dtype=bool)
+        base = (v["off"] + np.arange(N)[:, None, None] * v["sn"] + np.clip(hh, 0, None)[None, :, None] * v["sh"]
+                + np.clip(ww, 0, None)[None, None, :] * v["sw"])
+        base = np.where(ok, base, 0)
+        vals = flat[base[..., None] + np.arange(C)[None, None, None, :]]
+        return np.where(ok[..., None], vals, 0).reshape(-1, C)
+
+    DY = gather(dyf, plan.dy, 0, 0)[:, :plan.Cout]
+    for (dh, dw_, mf, tf) in plan.taps:
+        X = gather(xf, plan.views[mf], dh, dw_)[:, :plan.Cin]
+        G = X.T @ DY
+        idx = plan.dw_off + tf * plan.dw_stap + np.arange(plan.Cin)[:, None] * plan.dw_sci + np.arange(plan.Cout)[None, :]
+        dwf[idx] += G
+    return dw

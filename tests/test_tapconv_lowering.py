@@ -91,3 +91,26 @@ def test_same_pad_rules():
     for _ in range(6):
         sizes.append(-(-(sizes[-1] + 2) // 2))
     assert sizes == [128, 65, 34, 18, 10, 6, 4]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_wgrad_lowering(case):
+    N, H, W, Cs, k, s, pad, cout_real = case
+    cout = cout_real if cout_real % 8 == 0 else 16 * (-(-cout_real // 16))
+    rng = np.random.default_rng(2 + hash(case[:3]) % 1000)
+    cin = sum(Cs)
+    x = rng.normal(size=(N, H, W, cin))
+    w = torch.from_numpy(rng.normal(size=(k, k, cin, cout))).requires_grad_(True)
+    y = T.conv2d(torch.from_numpy(x), w, None, s, pad)
+    dy = rng.normal(size=tuple(y.shape))
+    y.backward(torch.from_numpy(dy))
+    ref = w.grad.numpy()
+    dw = np.zeros_like(ref)
+    c0 = 0
+    for C in Cs:
+        plan = tc.plan_conv_wgrad((N, H, W, C), k, s, pad, cout, cin_slice=(c0, c0 + C, cin))
+        emu.run_wgrad_plan(plan, np.ascontiguousarray(x[..., c0:c0 + C]), dy, dw)
+        d = plan.desc()
+        assert d.n_taps == k * k and d.Cin == C
+        c0 += C
+    np.testing.assert_allclose(dw, ref, rtol=1e-9, atol=1e-9)

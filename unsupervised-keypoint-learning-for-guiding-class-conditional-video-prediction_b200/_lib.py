@@ -32,6 +32,7 @@ SIGNATURES = {
     "kp_render_colorize_fwd": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp],
     "kp_colorize_fwd": [c_vp, c_vp, c_ll, c_int, c_vp, c_vp],
     "kp_tapconv_bf16": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "kp_tapconv_wgrad_bf16": [c_vp, c_vp, c_vp, c_vp, c_vp],
 }
 _RESTYPES = {"kp_last_error": ctypes.c_char_p, "kp_launch_count": ctypes.c_ulonglong}
 

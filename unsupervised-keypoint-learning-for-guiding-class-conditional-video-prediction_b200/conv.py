@@ -86,3 +86,16 @@ def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None
                   None if bias is None else bias.data_ptr(), out.data_ptr(),
                   None if ssum is None else ssum.data_ptr(), None if ssq is None else ssq.data_ptr(), _stream())
     return out
+
+
+def run_wgrad(plan, x, dy, dw, splits=0):
+    """Accumulate (+=) the weight gradient of one source into the f32 HWIO tensor `dw` (zero it first)."""
+    for t in (x, dy):
+        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+            raise ValueError("wgrad operands must be contiguous bf16 CUDA tensors")
+    if not (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()):
+        raise ValueError("dW must be a contiguous f32 CUDA tensor (HWIO)")
+    d = plan.desc(splits)
+    with torch.cuda.device(dw.device):
+        _lib.call("kp_tapconv_wgrad_bf16", ctypes.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream())
+    return dw

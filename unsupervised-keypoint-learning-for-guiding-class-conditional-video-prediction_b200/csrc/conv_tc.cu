@@ -261,27 +261,52 @@ static CUtensorMapSwizzle swizzle_for(int CB) {
     return CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-static int pow2_at_least(int v, int lo) {
-    int r = lo;
-    while (r < v) r <<= 1;
-    return r;
+// Encode a strided [N][Hd][Wd][C] bf16 view as a 4-D tiled tensor map with box {CB, TW, TH, TN}.
+int encode_view_map(CUtensorMap* out, const kp_tap_view& v, const void* src_base, int N, int CB, int TW, int TH, int TN,
+                    const char* what) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) return KP_ERR_DRIVER;
+    KP_REQUIRE(v.C > 0 && v.C % 8 == 0, "%s: channels %d must be a positive multiple of 8", what, v.C);
+    KP_REQUIRE(v.sw % 8 == 0 && v.sh % 8 == 0 && v.sn % 8 == 0 && v.off % 8 == 0,
+               "%s: strides/offset must be multiples of 8 elements (16 B)", what);
+    KP_REQUIRE(src_base != nullptr, "%s: NULL source", what);
+    const char* basep = reinterpret_cast<const char*>(src_base) + v.off * 2;
+    KP_REQUIRE((reinterpret_cast<uintptr_t>(basep) & 15) == 0, "%s: base not 16-byte aligned", what);
+    cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.Wd, (cuuint64_t)v.Hd, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+    cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(basep), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d N=%d box %d,%d,%d,%d)", what, (int)r, v.C, v.Wd,
+                  v.Hd, N, CB, TW, TH, TN);
+        return KP_ERR_DRIVER;
+    }
+    return KP_OK;
 }
 
-// pick TW,TH,TN (product 128, powers of two) minimising padded pixels
-static void choose_tile(int Wo, int Ho, int N, int* TW, int* TH, int* TN) {
+// pick TW,TH,TN (product `pixels`, powers of two) minimising padded pixels
+void choose_pixel_tile(int pixels, int Wo, int Ho, int N, int* TW, int* TH, int* TN) {
     long long best = -1;
-    for (int tw = 1; tw <= 128; tw <<= 1) {
-        for (int th = 1; tw * th <= 128; th <<= 1) {
-            const int tn = 128 / (tw * th);
+    for (int tw = 1; tw <= pixels; tw <<= 1) {
+        for (int th = 1; tw * th <= pixels; th <<= 1) {
+            const int tn = pixels / (tw * th);
             const long long cover = (long long)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th *
                                     ((N + tn - 1) / tn) * tn;
-            // prefer wide tiles on ties (longer contiguous runs for TMA and for the stores)
             if (best < 0 || cover < best || (cover == best && tw > *TW)) {
                 best = cover;
                 *TW = tw; *TH = th; *TN = tn;
             }
         }
     }
+}
+
+static int pow2_at_least(int v, int lo) {
+    int r = lo;
+    while (r < v) r <<= 1;
+    return r;
 }
 
 int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
@@ -299,7 +324,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     memset(&p, 0, sizeof(p));
     const int CB = d->CB;
     int TW = d->TW, TH = d->TH, TN = d->TN, BN = d->BN;
-    if (TW <= 0 || TH <= 0 || TN <= 0) choose_tile(d->Wo, d->Ho, d->N, &TW, &TH, &TN);
+    if (TW <= 0 || TH <= 0 || TN <= 0) choose_pixel_tile(128, d->Wo, d->Ho, d->N, &TW, &TH, &TN);
     KP_REQUIRE(TW * TH * TN == 128, "kp_tapconv: tile %dx%dx%d is not 128 pixels", TW, TH, TN);
     if (BN <= 0) {
         BN = d->Cout_pad <= 256 ? d->Cout_pad : (d->Cout_pad % 256 == 0 ? 256 : 128);
@@ -312,24 +337,9 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     int total_blocks_per_tap = -1;
     for (int m = 0; m < d->n_maps; ++m) {
         const kp_tap_view& v = d->map[m];
-        KP_REQUIRE(v.C > 0 && v.C % 8 == 0, "kp_tapconv: map %d channels %d must be a positive multiple of 8", m, v.C);
-        KP_REQUIRE(v.sw % 8 == 0 && v.sh % 8 == 0 && v.sn % 8 == 0 && v.off % 8 == 0,
-                   "kp_tapconv: map %d strides/offset must be multiples of 8 elements (16 B)", m);
-        KP_REQUIRE(v.src >= 0 && v.src < KP_MAX_MAPS && src[v.src] != nullptr, "kp_tapconv: map %d has no source", m);
-        const char* basep = reinterpret_cast<const char*>(src[v.src]) + v.off * 2;
-        KP_REQUIRE((reinterpret_cast<uintptr_t>(basep) & 15) == 0, "kp_tapconv: map %d base not 16-byte aligned", m);
-        cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.Wd, (cuuint64_t)v.Hd, (cuuint64_t)d->N};
-        cuuint64_t gstr[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
-        cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(&p.mapA[m], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(basep), gdim, gstr, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("kp_tapconv: cuTensorMapEncodeTiled(A map %d) failed with %d (C=%d W=%d H=%d N=%d)", m, (int)r, v.C,
-                      v.Wd, v.Hd, d->N);
-            return KP_ERR_DRIVER;
-        }
+        KP_REQUIRE(v.src >= 0 && v.src < KP_MAX_MAPS, "kp_tapconv: map %d has no source", m);
+        const int rc = encode_view_map(&p.mapA[m], v, src[v.src], d->N, CB, TW, TH, TN, "kp_tapconv A map");
+        if (rc != KP_OK) return rc;
         p.nblk[m] = (v.C + CB - 1) / CB;
     }
     int total_iters = 0;

@@ -1,0 +1,213 @@
+// Weight gradient of the tap-GEMM convolutions on tcgen05 tensor cores (sm_100a).
+//
+//   dW[tap][ci][co] += sum_pixels X_tap[pixel][ci] * dY[pixel][co]
+//
+// M = ci (128 rows per CTA), N = co (BN <= 256), K = pixels.  Both operands arrive exactly as in the forward
+// kernel - TMA 4-D boxes [64 pixels][CB channels], hardware swizzled - and are consumed as MN-major UMMA
+// operands (channels contiguous), so no transposed copy of X or dY exists anywhere.
+// grid = (ci blocks x co blocks, taps, pixel splits); fp32 partial tiles are accumulated into the HWIO
+// gradient with atomic adds.
+#include "kp_tc.cuh"
+#include "kp_internal.h"
+#include <string.h>
+
+namespace kp {
+
+static constexpr int WG_KP = 64;  // pixels per pipeline stage (GEMM-K 64 = 4 UMMA K-steps)
+
+struct alignas(64) WgradKParams {
+    CUtensorMap mapX[KP_MAX_MAPS];
+    CUtensorMap mapDY;
+    signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], mf[KP_MAX_TAPS];
+    int tap_flat[KP_MAX_TAPS];
+    int TW, TH, TN, tiles_w, tiles_h, total_tiles, tiles_per_split;
+    int Cin, Cout, BN, co_blocks, tmem_cols, stages;
+    uint32_t box_bytes, a_bytes, stage_bytes;
+    float* dw_out;
+    long long dw_off, dw_stap, dw_sci;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
+    constexpr uint32_t ROW_BYTES = CB * 2;
+    constexpr uint32_t SBO = 8 * ROW_BYTES;
+    constexpr uint32_t LAYOUT = (CB == 64) ? 2u : (CB == 32) ? 4u : 6u;
+    constexpr uint32_t KSTEP_BYTES = 16 * ROW_BYTES;  // 16 pixels per UMMA K-step
+
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* base = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)p.stages * p.stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const int ci0 = (blockIdx.x / p.co_blocks) * 128;
+    const int co0 = (blockIdx.x % p.co_blocks) * p.BN;
+    const int tap = blockIdx.y;
+    const int t_begin = blockIdx.z * p.tiles_per_split;
+    const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
+    const int n_iters = t_end - t_begin;  // host guarantees >= 1
+
+    const int n_a = min(128 / CB, (p.Cin - ci0 + CB - 1) / CB);
+    const int n_b = (min(p.BN, p.Cout - co0) + CB - 1) / CB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* mx = &p.mapX[p.mf[tap]];
+            tma_prefetch_desc(mx);
+            tma_prefetch_desc(&p.mapDY);
+            const int dh = p.dh[tap], dw = p.dw[tap];
+            const uint32_t tx = (uint32_t)(n_a + n_b) * p.box_bytes;
+            for (int it = 0; it < n_iters; ++it) {
+                const int tile = t_begin + it;
+                const int w0 = (tile % p.tiles_w) * p.TW;
+                const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+                const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
+                const int st = it % S;
+                if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
+                uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
+                uint8_t* b_dst = a_dst + p.a_bytes;
+                mbar_arrive_expect_tx(&full[st], tx);
+                for (int c = 0; c < n_a; ++c)
+                    tma_load_4d(a_dst + (size_t)c * p.box_bytes, mx, &full[st], ci0 + c * CB, w0 + dw, h0 + dh, n0);
+                for (int c = 0; c < n_b; ++c)
+                    tma_load_4d(b_dst + (size_t)c * p.box_bytes, &p.mapDY, &full[st], co0 + c * CB, w0, h0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);  // both operands MN-major
+            for (int it = 0; it < n_iters; ++it) {
+                const int st = it % S;
+                mbar_wait(&full[st], (it / S) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + (uint32_t)st * p.stage_bytes;
+                const uint32_t b_addr = a_addr + p.a_bytes;
+#pragma unroll
+                for (int kk = 0; kk < WG_KP / 16; ++kk) {
+                    const uint64_t da = umma_smem_desc(a_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
+                    const uint64_t db = umma_smem_desc(b_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
+                    umma_bf16(tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[st]);
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3;
+        const int ci = ci0 + q * 32 + lane;
+        const bool valid = ci < p.Cin;
+        float* orow = p.dw_out + p.dw_off + (long long)p.tap_flat[tap] * p.dw_stap + (long long)ci * p.dw_sci;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            float v[16];
+            __syncwarp();
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int co = co0 + c0 + j;
+                    if (co < p.Cout) atomicAdd(orow + co, v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    KP_REQUIRE(d->CB == 16 || d->CB == 32 || d->CB == 64, "kp_wgrad: CB must be 16, 32 or 64 (got %d)", d->CB);
+    KP_REQUIRE(d->n_maps >= 1 && d->n_maps <= KP_MAX_MAPS, "kp_wgrad: n_maps %d out of range", d->n_maps);
+    KP_REQUIRE(d->n_taps >= 1 && d->n_taps <= KP_MAX_TAPS, "kp_wgrad: n_taps %d out of range", d->n_taps);
+    KP_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cin > 0 && d->Cout > 0, "kp_wgrad: empty problem");
+    WgradKParams p;
+    memset(&p, 0, sizeof(p));
+    const int CB = d->CB;
+    choose_pixel_tile(WG_KP, d->Wo, d->Ho, d->N, &p.TW, &p.TH, &p.TN);
+    for (int m = 0; m < d->n_maps; ++m) {
+        const int rc = encode_view_map(&p.mapX[m], d->map[m], x, d->N, CB, p.TW, p.TH, p.TN, "kp_wgrad X map");
+        if (rc != KP_OK) return rc;
+    }
+    {
+        const int rc = encode_view_map(&p.mapDY, d->dy, dy, d->N, CB, p.TW, p.TH, p.TN, "kp_wgrad dY map");
+        if (rc != KP_OK) return rc;
+    }
+    for (int t = 0; t < d->n_taps; ++t) {
+        KP_REQUIRE(d->map_first[t] >= 0 && d->map_first[t] < d->n_maps, "kp_wgrad: tap %d map out of range", t);
+        p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.mf[t] = d->map_first[t]; p.tap_flat[t] = d->tap_flat[t];
+    }
+    p.tiles_w = (d->Wo + p.TW - 1) / p.TW;
+    p.tiles_h = (d->Ho + p.TH - 1) / p.TH;
+    p.total_tiles = p.tiles_w * p.tiles_h * ((d->N + p.TN - 1) / p.TN);
+    p.Cin = d->Cin; p.Cout = d->Cout;
+    const int cout_pad = (d->Cout + 15) / 16 * 16;
+    p.BN = cout_pad <= 256 ? cout_pad : 256;
+    p.co_blocks = (cout_pad + p.BN - 1) / p.BN;
+    const int ci_blocks = (d->Cin + 127) / 128;
+    int tm = 32;
+    while (tm < p.BN) tm <<= 1;
+    p.tmem_cols = tm;
+    p.box_bytes = (uint32_t)WG_KP * CB * 2u;
+    p.a_bytes = (uint32_t)(128 / CB) * p.box_bytes;                       // 16 KB
+    const uint32_t b_bytes = (uint32_t)((p.BN + CB - 1) / CB) * p.box_bytes;
+    p.stage_bytes = (p.a_bytes + b_bytes + 1023u) & ~1023u;
+    int splits = d->splits;
+    const int base_ctas = ci_blocks * p.co_blocks * d->n_taps;
+    if (splits <= 0) {
+        splits = (2 * 148 + base_ctas - 1) / base_ctas;
+        const int max_by_work = (p.total_tiles + 3) / 4;   // at least ~4 pixel tiles per CTA
+        if (splits > max_by_work) splits = max_by_work;
+    }
+    if (splits < 1) splits = 1;
+    if (splits > p.total_tiles) splits = p.total_tiles;
+    p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
+    splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    int stages = (int)((160u * 1024u) / p.stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    p.dw_out = dw;
+    p.dw_off = d->dw_off; p.dw_stap = d->dw_stap; p.dw_sci = d->dw_sci;
+
+    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)d->n_taps, (unsigned)splits);
+#define KP_LAUNCH_WGRAD(CBV)                                                                                     \
+    do {                                                                                                         \
+        static bool attr_done = false;                                                                           \
+        if (!attr_done) {                                                                                        \
+            KP_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                               227 * 1024));                                                     \
+            attr_done = true;                                                                                    \
+        }                                                                                                        \
+        wgrad_kernel<CBV><<<grid, 192, smem, st>>>(p);                                                           \
+    } while (0)
+    if (CB == 64) KP_LAUNCH_WGRAD(64);
+    else if (CB == 32) KP_LAUNCH_WGRAD(32);
+    else KP_LAUNCH_WGRAD(16);
+#undef KP_LAUNCH_WGRAD
+    KP_LAUNCHED();
+    return KP_OK;
+}
+
+}  // namespace kp

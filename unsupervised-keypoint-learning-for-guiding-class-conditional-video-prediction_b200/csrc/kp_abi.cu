@@ -105,3 +105,8 @@ int kp_tapconv_bf16(const kp_tapconv_desc* desc, const void* const* src, const v
 }
 
 }  // extern "C"
+
+extern "C" int kp_tapconv_wgrad_bf16(const kp_wgrad_desc* desc, const void* x, const void* dy, float* dw, void* stream) {
+    KP_NONNULL(desc); KP_NONNULL(x); KP_NONNULL(dy); KP_NONNULL(dw);
+    return kp::wgrad_launch(desc, x, dy, dw, static_cast<cudaStream_t>(stream));
+}

@@ -23,4 +23,7 @@ int k1_colorize(const float* maps, const float* colors, long long P, int K, floa
 int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
                    float* ssum, float* ssq, cudaStream_t st);
 
+// conv_wgrad.cu
+int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
+
 }  // namespace kp

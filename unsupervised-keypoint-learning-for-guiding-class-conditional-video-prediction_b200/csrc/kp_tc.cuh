@@ -6,6 +6,11 @@
 
 namespace kp {
 
+// host helpers defined in conv_tc.cu
+int encode_view_map(CUtensorMap* out, const kp_tap_view& v, const void* src_base, int N, int CB, int TW, int TH, int TN,
+                    const char* what);
+void choose_pixel_tile(int pixels, int Wo, int Ho, int N, int* TW, int* TH, int* TN);
+
 // ---- TMA tensor loads (tile mode) ------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -234,3 +234,68 @@ def plan_conv_dgrad(x_shape, k, stride, pad, cout, cin_slice=None):
         _finish(p, Cx, "dgrad", [kh * k + kw for kh, kw in tap_k], [(0, cout)], row_slice=(c0, c1))
         plans.append(p)
     return plans
+
+
+# ------------------------------------------------------------------------------------------------
+# weight gradient
+# ------------------------------------------------------------------------------------------------
+class WgradDesc(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("n_maps", ctypes.c_int), ("map", TapView * KP_MAX_MAPS), ("dy", TapView),
+                ("n_taps", ctypes.c_int),
+                ("dh", ctypes.c_byte * KP_MAX_TAPS), ("dw", ctypes.c_byte * KP_MAX_TAPS),
+                ("map_first", ctypes.c_byte * KP_MAX_TAPS), ("tap_flat", ctypes.c_int * KP_MAX_TAPS),
+                ("CB", ctypes.c_int), ("Ho", ctypes.c_int), ("Wo", ctypes.c_int),
+                ("Cin", ctypes.c_int), ("Cout", ctypes.c_int),
+                ("dw_off", ctypes.c_longlong), ("dw_stap", ctypes.c_longlong), ("dw_sci", ctypes.c_longlong),
+                ("splits", ctypes.c_int)]
+
+
+class WgradPlan:
+    """dW[kh,kw,c0:c1,:] of one concat source: X views + taps (as in the forward plan) and the dY view."""
+
+    def __init__(self):
+        self.N = 0
+        self.views = []
+        self.dy = None
+        self.taps = []       # (dh, dw, map, tap_flat)
+        self.CB = 16
+        self.Ho = self.Wo = 0
+        self.Cin = self.Cout = 0
+        self.dw_off = self.dw_stap = self.dw_sci = 0
+
+    def desc(self, splits=0):
+        d = WgradDesc()
+        d.N = self.N
+        d.n_maps = len(self.views)
+        for i, v in enumerate(self.views):
+            d.map[i].src, d.map[i].C, d.map[i].Wd, d.map[i].Hd = 0, v["C"], v["Wd"], v["Hd"]
+            d.map[i].off, d.map[i].sw, d.map[i].sh, d.map[i].sn = v["off"], v["sw"], v["sh"], v["sn"]
+        v = self.dy
+        d.dy.src, d.dy.C, d.dy.Wd, d.dy.Hd = 0, v["C"], v["Wd"], v["Hd"]
+        d.dy.off, d.dy.sw, d.dy.sh, d.dy.sn = v["off"], v["sw"], v["sh"], v["sn"]
+        d.n_taps = len(self.taps)
+        for i, (dh, dw, mf, tf) in enumerate(self.taps):
+            d.dh[i], d.dw[i], d.map_first[i], d.tap_flat[i] = dh, dw, mf, tf
+        d.CB, d.Ho, d.Wo, d.Cin, d.Cout = self.CB, self.Ho, self.Wo, self.Cin, self.Cout
+        d.dw_off, d.dw_stap, d.dw_sci = self.dw_off, self.dw_stap, self.dw_sci
+        d.splits = splits
+        return d
+
+
+def plan_conv_wgrad(x_shape, k, stride, pad, cout, cin_slice=None):
+    """Weight gradient w.r.t. the [k,k,cin_total,cout] HWIO kernel rows [c0,c1) given X = one source
+    [N,H,W,C] and dY [N,Ho,Wo,cout] (cout must be a multiple of 8 in memory)."""
+    N, H, W, Cx = x_shape
+    c0, c1, cin_total = (0, Cx, Cx) if cin_slice is None else cin_slice
+    assert c1 - c0 == Cx
+    fwd, (_, Ho, Wo) = plan_conv_fwd([x_shape], k, stride, pad, cout)
+    p = WgradPlan()
+    p.N = N
+    p.views = fwd.views
+    p.taps = [(dh, dw, mf, tf) for (dh, dw, mf), tf in zip(fwd.taps, fwd.pack["taps"])]
+    p.dy = dict(src=0, C=cout, Wd=Wo, Hd=Ho, off=0, sw=cout, sh=Wo * cout, sn=Ho * Wo * cout)
+    p.CB = pick_cb([Cx, cout])
+    p.Ho, p.Wo = Ho, Wo
+    p.Cin, p.Cout = Cx, cout
+    p.dw_off, p.dw_stap, p.dw_sci = c0 * cout, cin_total * cout, cout
+    return p
