@@ -126,6 +126,7 @@ typedef struct {
     int Cout;                                /* channels written per pixel */
     int out_f32;                             /* 0: bf16 output, 1: f32 output */
     int act; float alpha;
+    int accumulate;                          /* != 0: out += result instead of out = result */
     int TW, TH, TN, BN;                      /* tile: TW*TH*TN == 128 pixels x BN channels; 0 = let the library choose */
 } kp_tapconv_desc;
 
@@ -159,6 +160,67 @@ typedef struct {
 } kp_wgrad_desc;
 
 int kp_tapconv_wgrad_bf16(const kp_wgrad_desc* desc, const void* x, const void* dy, float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Memory-bound companions (bf16 NHWC, 8-channel vectors; fp32 only at the reference boundary)
+ * ------------------------------------------------------------------------------------------- */
+
+/* f32 image [P,3] -> bf16 [P,16]: out[c] = a[c]*x[perm[c]] + b[c] for c<3, zeros above.  Network inputs use the
+ * identity; the VGG input folds (x+1)/2*255, RGB->BGR and the mean subtraction
+ * (models/detector_translator_model.py:262-263, models/networks/vgg.py:17-19).  a, b, perm are HOST arrays. */
+int kp_image_prep(const float* x, long long P, const float* a, const float* b, const int* perm, void* out, void* stream);
+/* its adjoint: g bf16 [P,16] -> dx f32 [P,3] (accumulate != 0: +=). */
+int kp_image_prep_bwd(const void* g, long long P, const float* a, const int* perm, int accumulate, float* dx, void* stream);
+
+/* tf.contrib.layers.batch_norm (models/networks/layers.py:13-14), training mode, split around the convolution:
+ * the conv epilogue accumulates per-channel sum / sum-of-squares of its PRE-bias accumulators
+ * (kp_tapconv_bf16 stats_*); kp_bn_finalize turns them into scale/shift (normalising with the biased
+ * variance), saves mean/rstd for the backward pass and updates the moving averages (unbiased variance,
+ * moving = moving*decay + batch*(1-decay)); moving_mean/moving_var may be NULL (no update).          */
+int kp_bn_finalize(const float* stats_sum, const float* stats_sq, const float* conv_bias, const float* gamma,
+                   const float* beta, int C, double count, float eps, float decay, float* moving_mean, float* moving_var,
+                   float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);
+/* y = relu?(x*scale + shift) (scale NULL = identity), optionally followed by tf.image.resize_images x2 (legacy
+ * bilinear, models/networks/__init__.py:63,98): x bf16 [N,H,W,C] -> out bf16 [N,H,W,C] or [N,2H,2W,C].  */
+int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W,
+                    int C, void* out, void* stream);
+/* backward of kp_bn_act_apply + batch-norm statistics: dout (grad of the output, upsampled size if upsample),
+ * x (the conv output saved by the forward) -> dbeta, dgamma f32 [C] and dx bf16 [N,H,W,C].            */
+int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
+                  const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
+                  void* dx, void* stream);
+/* g = dy * (y > 0 ? 1 : alpha): backward of the fused bias+ReLU / bias+leaky_relu epilogues. */
+int kp_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, void* stream);
+/* tf.nn.max_pool 2x2 s2 (models/networks/vgg.py:45-46) and its backward (gradient to the first maximum; with
+ * relu_mask the ReLU mask of the pooled tensor's producer is applied in the same pass).               */
+int kp_maxpool2x2_fwd(const void* x, int N, int H, int W, int C, void* out, void* stream);
+int kp_maxpool2x2_bwd(const void* dy, const void* x, int relu_mask, int N, int H, int W, int C, void* dx, void* stream);
+/* final = im*mask + crude*(1-mask) (models/detector_translator_model.py:174; clip != 0 adds the clip_by_value
+ * of models/final_model.py:98-99).  heads f32 [P,4] = (crude, sigmoid(mask)) from the fused head conv.  */
+int kp_mask_compose_fwd(const float* heads, const float* im, long long P, int clip, float* final_out, float* crude_out,
+                        float* mask_out, void* stream);
+/* d_final f32 [P,3] -> gradient w.r.t. the head pre-activations, bf16 [P,8]. */
+int kp_mask_compose_bwd(const float* d_final, const float* heads, const float* im, long long P, void* d_heads, void* stream);
+/* tf.concat on channels with cast to bf16 and zero padding to Ctot (joint embedding,
+ * models/detector_translator_model.py:170), and its adjoint.  src/C/is_f32 are HOST arrays.          */
+int kp_pack_channels(const void* const* src, const int* C, const int* is_f32, int n, long long P, int Ctot, void* out,
+                     void* stream);
+int kp_unpack_channels(const void* g, long long P, int Ctot, void* const* dst, const int* C, const int* is_f32, int n,
+                       void* stream);
+/* L1 feature loss between the gt and the pred VGG features (two bf16 tensors of n_elems each;
+ * models/detector_translator_model.py:280-287): *loss += weight*mean|gt-pred|; d_pred (nullable) receives
+ * weight/count*sign(pred-gt).                                                                        */
+int kp_l1_pair_fwd_bwd(const void* feat_gt, const void* feat_pred, long long n_elems, float weight, float* loss,
+                       void* d_pred, void* stream);
+/* sigmoid_cross_entropy_with_logits vs a constant label (models/detector_translator_model.py:249-254,265-267):
+ * *loss += weight*mean(...); d_logits (nullable) bf16 [n,8], channel 0 = weight/n*(sigmoid(x)-label). */
+int kp_bce_logits_fwd_bwd(const float* logits, int n, float label, float weight, float* loss, void* d_logits, void* stream);
+/* tf.train.AdamOptimizer update over one flat buffer (models/detector_translator_model.py:198-202):
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t); p -= lr_t*m/(sqrt(v)+eps); grads are multiplied by grad_scale first. */
+int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+               int t, float grad_scale, void* stream);
+/* out[c] += sum over pixels of g bf16 [P,C] (bias gradients). */
+int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,12 @@ this package is the host-side mirror of the reference's ``utils`` / ``models.net
 """
 from . import _lib  # noqa: F401
 from . import k1  # noqa: F401
+from . import tapconv  # noqa: F401
+from . import conv  # noqa: F401
+from . import ops  # noqa: F401
+from . import engine  # noqa: F401
 from .utils import model as model_utils  # noqa: F401
+from . import networks  # noqa: F401
+from . import models  # noqa: F401
 
-__all__ = ["model_utils", "k1"]
+__all__ = ["model_utils", "k1", "networks", "models", "engine", "ops", "conv", "tapconv"]

@@ -33,6 +33,24 @@ SIGNATURES = {
     "kp_colorize_fwd": [c_vp, c_vp, c_ll, c_int, c_vp, c_vp],
     "kp_tapconv_bf16": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "kp_tapconv_wgrad_bf16": [c_vp, c_vp, c_vp, c_vp, c_vp],
+    "kp_image_prep": [c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "kp_image_prep_bwd": [c_vp, c_ll, c_vp, c_vp, c_int, c_vp, c_vp],
+    "kp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_double, c_float, c_float, c_vp, c_vp, c_vp, c_vp,
+                       c_vp, c_vp, c_vp],
+    "kp_bn_act_apply": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "kp_bn_act_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                      c_vp],
+    "kp_act_mask_bwd": [c_vp, c_vp, c_float, c_ll, c_vp, c_vp],
+    "kp_maxpool2x2_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "kp_maxpool2x2_bwd": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "kp_mask_compose_fwd": [c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp],
+    "kp_mask_compose_bwd": [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp],
+    "kp_pack_channels": [c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_vp, c_vp],
+    "kp_unpack_channels": [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
+    "kp_l1_pair_fwd_bwd": [c_vp, c_vp, c_ll, c_float, c_vp, c_vp, c_vp],
+    "kp_bce_logits_fwd_bwd": [c_vp, c_int, c_float, c_float, c_vp, c_vp, c_vp],
+    "kp_adam_tf": [c_vp, c_vp, c_vp, c_vp, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, c_vp],
+    "kp_channel_sum": [c_vp, c_ll, c_int, c_vp, c_vp],
 }
 _RESTYPES = {"kp_last_error": ctypes.c_char_p, "kp_launch_count": ctypes.c_ulonglong}
 

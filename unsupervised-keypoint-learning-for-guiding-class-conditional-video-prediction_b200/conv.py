@@ -59,7 +59,8 @@ def pad_vec(v, n):
     return torch.nn.functional.pad(v, (0, n - v.shape[0])).contiguous()
 
 
-def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None, cout_written=None, tile=None, bn=0):
+def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None, cout_written=None, tile=None, bn=0,
+             accumulate=False):
     """Launch one tap-GEMM.  srcs: bf16 NHWC CUDA tensors; out: bf16 or f32 tensor written through the plan's
     output view; bias: f32 [rows_pad] or None; stats: (sum, sumsq) f32 [rows_pad] accumulators or None."""
     for s in srcs:
@@ -72,7 +73,8 @@ def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None
         raise ValueError("output must be a bf16 or f32 CUDA tensor")
     if bias is not None and (bias.dtype != torch.float32 or bias.shape[0] != plan.rows_pad):
         raise ValueError("bias must be f32 [rows_pad]")
-    d = plan.desc(act=act, alpha=alpha, out_f32=(out.dtype == torch.float32), cout_written=cout_written, tile=tile, bn=bn)
+    d = plan.desc(act=act, alpha=alpha, out_f32=(out.dtype == torch.float32), cout_written=cout_written, tile=tile, bn=bn,
+                  accumulate=accumulate)
     ptrs = (ctypes.c_void_p * tc.KP_MAX_MAPS)()
     for i, s in enumerate(srcs):
         ptrs[i] = s.data_ptr()

@@ -31,7 +31,7 @@ struct alignas(64) TapConvKParams {
     uint32_t a_bytes, b_bytes, stage_bytes;
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
-    int Cout, out_f32, act;
+    int Cout, out_f32, act, accumulate;
     float alpha;
     const float* bias;
     float* ssum;
@@ -202,6 +202,30 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act, p.alpha, ch0 + j == p.Cout - 1);
             }
             const int nvalid = min(16, p.Cout - ch0);
+            if (p.accumulate) {  // out += result (gradient of a tensor with several consumers)
+                if (p.out_f32) {
+                    const float* o = reinterpret_cast<const float*>(p.out) + pix + ch0;
+                    for (int j = 0; j < nvalid; ++j) v[j] += o[j];
+                } else {
+                    const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.out) + pix + ch0;
+                    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                        float old[16];
+                        const uint4* o4 = reinterpret_cast<const uint4*>(o);
+                        const uint4 u0 = o4[0], u1 = o4[1];
+                        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+                        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 a = __bfloat1622float2(h0[j]), b = __bfloat1622float2(h1[j]);
+                            old[2 * j] = a.x; old[2 * j + 1] = a.y; old[8 + 2 * j] = b.x; old[8 + 2 * j + 1] = b.y;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += old[j];
+                    } else {
+                        for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(o[j]);
+                    }
+                }
+            }
             if (p.out_f32) {
                 float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
                 if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -388,7 +412,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.stages = stages;
     p.out = out;
     p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
-    p.Cout = d->Cout; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha;
+    p.Cout = d->Cout; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate;
     p.bias = bias; p.ssum = ssum; p.ssq = ssq;
 
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;

@@ -1,0 +1,739 @@
+// Memory-bound companions of the convolution engine (sm_100a): batch-norm statistics/apply/backward,
+// legacy-bilinear x2 upsampling (fused into the BN+ReLU pass), max-pool, image packing, mask compose,
+// channel pack/unpack, losses and the TF-style Adam update.  Everything is bf16 NHWC with 16-byte
+// (8-channel) vector accesses unless the reference boundary demands fp32.
+//
+// Reference ops replaced (all under /root/reference):
+//   tf.contrib.layers.batch_norm + tf.nn.relu    models/networks/layers.py:13-14, networks/__init__.py:11-12...
+//   tf.image.resize_images (legacy bilinear x2)  models/networks/__init__.py:63,98
+//   tf.nn.max_pool 2x2 s2                        models/networks/vgg.py:45-46
+//   im*mask + crude*(1-mask), clip               models/detector_translator_model.py:174, final_model.py:96-99
+//   VGG preprocessing                            detector_translator_model.py:262-263, vgg.py:17-19
+//   tf.concat for the joint embedding            detector_translator_model.py:170
+//   L1 feature loss / BCE-with-logits            detector_translator_model.py:249-254,265-267,280-287
+//   tf.train.AdamOptimizer                       detector_translator_model.py:198-202
+#include "kp_common.cuh"
+#include "kp_internal.h"
+#include <math.h>
+
+namespace kp {
+
+struct bf8 {  // eight bf16 values = one 16-byte vector
+    uint4 u;
+};
+__device__ __forceinline__ void bf8_unpack(const uint4& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float* f) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+static inline int grid_for(long long work_items, int block, int max_blocks = 148 * 16) {
+    long long b = (work_items + block - 1) / block;
+    if (b > max_blocks) b = max_blocks;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// =============================================================================================
+// image packing: f32 [P,3] -> bf16 [P,16], out[c] = a[c]*x[perm[c]] + b[c] (c<3), 0 for c>=3
+// =============================================================================================
+struct ImgPrep {
+    float a[3], b[3];
+    int perm[3];
+};
+__global__ void image_prep_kernel(const float* __restrict__ x, long long P, ImgPrep q, __nv_bfloat16* __restrict__ out) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const float v0 = x[3 * p], v1 = x[3 * p + 1], v2 = x[3 * p + 2];
+        const float in[3] = {v0, v1, v2};
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] = fmaf(q.a[c], in[q.perm[c]], q.b[c]);
+        uint4* o = reinterpret_cast<uint4*>(out + 16 * p);
+        o[0] = bf8_pack(f);
+        o[1] = make_uint4(0, 0, 0, 0);
+    }
+}
+// backward: g bf16 [P,16] -> dx f32 [P,3]: dx[perm[c]] (+)= a[c]*g[c]
+__global__ void image_prep_bwd_kernel(const __nv_bfloat16* __restrict__ g, long long P, ImgPrep q, int accumulate,
+                                      float* __restrict__ dx) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        float f[8];
+        bf8_unpack(*reinterpret_cast<const uint4*>(g + 16 * p), f);
+        float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[q.perm[c]] = q.a[c] * f[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dx[3 * p + c] = accumulate ? dx[3 * p + c] + o[c] : o[c];
+    }
+}
+
+// =============================================================================================
+// batch norm
+// =============================================================================================
+// finalize: stats of the PRE-bias accumulators -> scale/shift for y = conv+bias, saved mean/rstd, moving averages.
+__global__ void bn_finalize_kernel(const float* __restrict__ ssum, const float* __restrict__ ssq, const float* __restrict__ bias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int C, float count,
+                                   float eps, float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m0 = (double)ssum[c] / count;
+    double var = (double)ssq[c] / count - m0 * m0;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)m0 + (bias ? bias[c] : 0.f);
+    const float rstd = rsqrtf((float)var + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (save_mean) save_mean[c] = mean;
+    if (save_rstd) save_rstd[c] = rstd;
+    if (moving_mean) {
+        const float unbiased = (float)(var * (count / fmax(count - 1.0, 1.0)));
+        moving_mean[c] = moving_mean[c] * decay + mean * (1.f - decay);
+        moving_var[c] = moving_var[c] * decay + unbiased * (1.f - decay);
+    }
+}
+
+// y = relu(x*scale + shift) (scale == nullptr: identity), optionally followed by the legacy bilinear x2
+// upsampling (out[2i] = in[i], out[2i+1] = (in[i] + in[min(i+1,n-1)])/2 on each axis).
+template <bool UPSAMPLE>
+__global__ void bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int relu, int N, int H, int W, int C,
+                                    __nv_bfloat16* __restrict__ out) {
+    const int CG = C >> 3;
+    const int Ho = UPSAMPLE ? 2 * H : H, Wo = UPSAMPLE ? 2 * W : W;
+    const long long total = (long long)N * Ho * Wo * CG;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % CG);
+        long long pix = idx / CG;
+        const int wo = (int)(pix % Wo);
+        pix /= Wo;
+        const int ho = (int)(pix % Ho);
+        const int n = (int)(pix / Ho);
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = scale ? scale[cg * 8 + j] : 1.f;
+            sh[j] = scale ? shift[cg * 8 + j] : 0.f;
+        }
+        auto load = [&](int h, int w, float* f) {
+            bf8_unpack(*reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + cg * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                f[j] = fmaf(f[j], sc[j], sh[j]);
+                if (relu) f[j] = fmaxf(f[j], 0.f);
+            }
+        };
+        float r[8];
+        if (!UPSAMPLE) {
+            load(ho, wo, r);
+        } else {
+            const int h0 = ho >> 1, w0 = wo >> 1;
+            const int h1 = min(h0 + (ho & 1), H - 1), w1 = min(w0 + (wo & 1), W - 1);
+            float a[8], b[8], c[8], d[8];
+            load(h0, w0, a);
+            if (wo & 1) load(h0, w1, b);
+            if (ho & 1) load(h1, w0, c);
+            if ((ho & 1) && (wo & 1)) load(h1, w1, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // TF computes top/bottom row lerps along x first, then the lerp along y
+                const float top = (wo & 1) ? a[j] + (b[j] - a[j]) * 0.5f : a[j];
+                if (ho & 1) {
+                    const float bot = (wo & 1) ? c[j] + (d[j] - c[j]) * 0.5f : c[j];
+                    r[j] = top + (bot - top) * 0.5f;
+                } else {
+                    r[j] = top;
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(out + idx * 8) = bf8_pack(r);
+    }
+}
+
+// Gradient arriving at the (un-upsampled) activation a = relu(z): for UPSAMPLE the adjoint of the x2 resize is
+// gathered from the 3x3 neighbourhood of dOut [N,2H,2W,C].
+template <bool UPSAMPLE>
+__device__ __forceinline__ void gather_dact(const __nv_bfloat16* __restrict__ dout, int n, int h, int w, int cg, int H, int W,
+                                            int C, float* g) {
+    if (!UPSAMPLE) {
+        bf8_unpack(*reinterpret_cast<const uint4*>(dout + (((long long)n * H + h) * W + w) * C + cg * 8), g);
+        return;
+    }
+    const int Ho = 2 * H, Wo = 2 * W;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    // 1-D weights of out rows {2h-1, 2h, 2h+1} on in row h: 0.5 (if h>=1), 1, 0.5 (+0.5 more if h == H-1)
+    float wy[3] = {h >= 1 ? 0.5f : 0.f, 1.f, h == H - 1 ? 1.f : 0.5f};
+    float wx[3] = {w >= 1 ? 0.5f : 0.f, 1.f, w == W - 1 ? 1.f : 0.5f};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int oh = 2 * h - 1 + dy;
+        if (oh < 0 || oh >= Ho || wy[dy] == 0.f) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int ow = 2 * w - 1 + dx;
+            if (ow < 0 || ow >= Wo || wx[dx] == 0.f) continue;
+            float t[8];
+            bf8_unpack(*reinterpret_cast<const uint4*>(dout + (((long long)n * Ho + oh) * Wo + ow) * C + cg * 8), t);
+            const float wgt = wy[dy] * wx[dx];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = fmaf(wgt, t[j], g[j]);
+        }
+    }
+}
+
+// pass 1 of the BN+ReLU(+upsample) backward: dbeta[c] += sum g, dgamma[c] += sum g*xhat  (g = dAct * (z>0))
+template <bool UPSAMPLE>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, int relu, int N, int H, int W, int C, float* __restrict__ dbeta,
+                         float* __restrict__ dgamma) {
+    const int CG = C >> 3;                 // power of two, <= 256
+    const int cg = threadIdx.x % CG;
+    const int lanes = blockDim.x / CG;     // pixel lanes per block
+    const int pl = threadIdx.x / CG;
+    const long long P = (long long)N * H * W;
+    float sc[8], sh[8], mu[8], rs[8], sb[8], sg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[cg * 8 + j]; sh[j] = shift[cg * 8 + j];
+        mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
+        sb[j] = 0.f; sg[j] = 0.f;
+    }
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
+        const int w = (int)(p % W);
+        const int h = (int)((p / W) % H);
+        const int n = (int)(p / ((long long)W * H));
+        float g[8], xv[8];
+        gather_dact<UPSAMPLE>(dout, n, h, w, cg, H, W, C, g);
+        bf8_unpack(*reinterpret_cast<const uint4*>(x + p * C + cg * 8), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(xv[j], sc[j], sh[j]);
+            const float gj = (relu && z <= 0.f) ? 0.f : g[j];
+            sb[j] += gj;
+            sg[j] = fmaf(gj, (xv[j] - mu[j]) * rs[j], sg[j]);
+        }
+    }
+    __shared__ float red[2][256 * 8 / 1];  // [2][threads][8] would be 16 KB; reuse by striding below
+    // reduce over pixel lanes sharing a channel group
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[0][threadIdx.x * 8 + j] = sb[j];
+        red[1][threadIdx.x * 8 + j] = sg[j];
+    }
+    __syncthreads();
+    if (pl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sb[j] += red[0][(l * CG + cg) * 8 + j];
+                sg[j] += red[1][(l * CG + cg) * 8 + j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(dbeta + cg * 8 + j, sb[j]);
+            atomicAdd(dgamma + cg * 8 + j, sg[j]);
+        }
+    }
+}
+
+// pass 2: dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n)   (bf16), gamma*rstd == scale
+template <bool UPSAMPLE>
+__global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const float* __restrict__ dbeta, const float* __restrict__ dgamma, int relu, int N,
+                                        int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+    const int CG = C >> 3;
+    const long long total = (long long)N * H * W * CG;
+    const float inv_n = 1.0f / (float)((long long)N * H * W);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % CG);
+        const long long p = idx / CG;
+        const int w = (int)(p % W);
+        const int h = (int)((p / W) % H);
+        const int n = (int)(p / ((long long)W * H));
+        float g[8], xv[8], r[8];
+        gather_dact<UPSAMPLE>(dout, n, h, w, cg, H, W, C, g);
+        bf8_unpack(*reinterpret_cast<const uint4*>(x + p * C + cg * 8), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            const float sc = scale[c];
+            const float z = fmaf(xv[j], sc, shift[c]);
+            const float gj = (relu && z <= 0.f) ? 0.f : g[j];
+            const float xhat = (xv[j] - mean[c]) * rstd[c];
+            r[j] = sc * (gj - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n);
+        }
+        *reinterpret_cast<uint4*>(dx + idx * 8) = bf8_pack(r);
+    }
+}
+
+// =============================================================================================
+// activation-mask backward for bias+ReLU / bias+leaky layers (VGG, img_discr): g = dy * (y > 0 ? 1 : alpha)
+// =============================================================================================
+__global__ void act_mask_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, float alpha,
+                                    long long nvec, __nv_bfloat16* __restrict__ g) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        bf8_unpack(reinterpret_cast<const uint4*>(dy)[i], a);
+        bf8_unpack(reinterpret_cast<const uint4*>(y)[i], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = b[j] > 0.f ? a[j] : alpha * a[j];
+        reinterpret_cast<uint4*>(g)[i] = bf8_pack(a);
+    }
+}
+
+// =============================================================================================
+// max pool 2x2 stride 2 (even H, W)
+// =============================================================================================
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                   __nv_bfloat16* __restrict__ out) {
+    const int CG = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const long long total = (long long)N * Ho * Wo * CG;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % CG);
+        long long pix = idx / CG;
+        const int wo = (int)(pix % Wo);
+        pix /= Wo;
+        const int ho = (int)(pix % Ho);
+        const int n = (int)(pix / Ho);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float t[8];
+                bf8_unpack(*reinterpret_cast<const uint4*>(x + (((long long)n * H + 2 * ho + dy) * W + 2 * wo + dx) * C + cg * 8), t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], t[j]);
+            }
+        *reinterpret_cast<uint4*>(out + idx * 8) = bf8_pack(m);
+    }
+}
+// dX[window] = dY routed to the first maximum of the window, times the ReLU mask of x (x > 0) when relu_mask.
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, int relu_mask,
+                                   int N, int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+    const int CG = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const long long total = (long long)N * Ho * Wo * CG;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % CG);
+        long long pix = idx / CG;
+        const int wo = (int)(pix % Wo);
+        pix /= Wo;
+        const int ho = (int)(pix % Ho);
+        const int n = (int)(pix / Ho);
+        float g[8], t[4][8];
+        bf8_unpack(*reinterpret_cast<const uint4*>(dy + idx * 8), g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            bf8_unpack(*reinterpret_cast<const uint4*>(x + (((long long)n * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1)) * C + cg * 8), t[k]);
+        float o[4][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int best = 0;
+            float bv = t[0][j];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (t[k][j] > bv) { bv = t[k][j]; best = k; }
+            const float gj = ((relu_mask & 1) && bv <= 0.f) ? 0.f : g[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][j] = (k == best) ? gj : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4* dst = reinterpret_cast<uint4*>(dx + (((long long)n * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1)) * C + cg * 8);
+            if (relu_mask & 2) {  // accumulate into an existing gradient (a feature that also feeds the L1 loss)
+                float old[8];
+                bf8_unpack(*dst, old);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[k][j] += old[j];
+            }
+            *dst = bf8_pack(o[k]);
+        }
+    }
+}
+
+// =============================================================================================
+// mask compose: heads f32 [P,4] = (crude rgb, mask in (0,1)), im f32 [P,3] -> final = im*m + crude*(1-m)
+// =============================================================================================
+__global__ void compose_fwd_kernel(const float* __restrict__ heads, const float* __restrict__ im, long long P, int clip,
+                                   float* __restrict__ final_out, float* __restrict__ crude_out, float* __restrict__ mask_out) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const float4 hd = reinterpret_cast<const float4*>(heads)[p];
+        const float m = hd.w;
+        const float cr[3] = {hd.x, hd.y, hd.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float f = im[3 * p + c] * m + cr[c] * (1.f - m);
+            float cc = cr[c];
+            if (clip) {
+                f = fminf(fmaxf(f, -1.f), 1.f);
+                cc = fminf(fmaxf(cc, -1.f), 1.f);
+            }
+            final_out[3 * p + c] = f;
+            if (crude_out) crude_out[3 * p + c] = cc;
+        }
+        if (mask_out) mask_out[p] = m;
+    }
+}
+// d_final f32 [P,3] -> gradient w.r.t. the head PRE-activations, bf16 [P,8] (crude 3, mask logit 1, 4 zeros)
+__global__ void compose_bwd_kernel(const float* __restrict__ d_final, const float* __restrict__ heads,
+                                   const float* __restrict__ im, long long P, __nv_bfloat16* __restrict__ d_heads) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const float4 hd = reinterpret_cast<const float4*>(heads)[p];
+        const float m = hd.w;
+        const float cr[3] = {hd.x, hd.y, hd.z};
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float dm = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float g = d_final[3 * p + c];
+            f[c] = g * (1.f - m);
+            dm = fmaf(g, im[3 * p + c] - cr[c], dm);
+        }
+        f[3] = dm * m * (1.f - m);
+        *reinterpret_cast<uint4*>(d_heads + 8 * p) = bf8_pack(f);
+    }
+}
+
+// =============================================================================================
+// channel pack / unpack (joint embedding): up to 3 sources (bf16 or f32) -> bf16 [P, Ctot] zero padded
+// =============================================================================================
+struct PackSrc {
+    const void* ptr[3];
+    int C[3];
+    int is_f32[3];
+    int n;
+};
+__global__ void pack_channels_kernel(PackSrc s, long long P, int Ctot, __nv_bfloat16* __restrict__ out) {
+    const long long total = P * Ctot;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / Ctot;
+        int c = (int)(idx - p * Ctot);
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (i < s.n) {
+                if (c >= 0 && c < s.C[i]) {
+                    v = s.is_f32[i] ? reinterpret_cast<const float*>(s.ptr[i])[p * s.C[i] + c]
+                                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.ptr[i])[p * s.C[i] + c]);
+                }
+                c -= s.C[i];
+            }
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+struct UnpackDst {
+    void* ptr[3];
+    int C[3];
+    int is_f32[3];
+    int n;
+};
+__global__ void unpack_channels_kernel(const __nv_bfloat16* __restrict__ g, long long P, int Ctot, UnpackDst d) {
+    const long long total = P * Ctot;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / Ctot;
+        int c = (int)(idx - p * Ctot);
+        const __nv_bfloat16 v = g[idx];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (i < d.n) {
+                if (c >= 0 && c < d.C[i]) {
+                    if (d.is_f32[i]) reinterpret_cast<float*>(d.ptr[i])[p * d.C[i] + c] = __bfloat162float(v);
+                    else reinterpret_cast<__nv_bfloat16*>(d.ptr[i])[p * d.C[i] + c] = v;
+                }
+                c -= d.C[i];
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// losses
+// =============================================================================================
+// L1 feature loss between the two halves of a bf16 feature tensor [2*half]: loss += weight * mean|gt - pred|,
+// d_pred = weight/count * sign(pred - gt)   (bf16, may be nullptr)
+__global__ void __launch_bounds__(256)
+l1_pair_kernel(const __nv_bfloat16* __restrict__ feat_gt, const __nv_bfloat16* __restrict__ feat_pred, long long half_vec,
+               float weight_over_count, float* __restrict__ loss, __nv_bfloat16* __restrict__ d_pred) {
+    float acc = 0.f;
+    const uint4* gt = reinterpret_cast<const uint4*>(feat_gt);
+    const uint4* pr = reinterpret_cast<const uint4*>(feat_pred);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half_vec; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8], g[8];
+        bf8_unpack(gt[i], a);
+        bf8_unpack(pr[i], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = b[j] - a[j];
+            acc += fabsf(d);
+            g[j] = d > 0.f ? weight_over_count : (d < 0.f ? -weight_over_count : 0.f);
+        }
+        if (d_pred) reinterpret_cast<uint4*>(d_pred)[i] = bf8_pack(g);
+    }
+    acc = warp_sum(acc);
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+        atomicAdd(loss, t * weight_over_count);
+    }
+}
+
+// BCE with logits against a constant label z: loss += weight*mean(max(x,0) - x z + log1p(exp(-|x|)));
+// d_logits bf16 [n,8] (channel 0 = weight/n * (sigmoid(x) - z), rest zero) for the D_logit conv backward.
+__global__ void __launch_bounds__(256)
+bce_logits_kernel(const float* __restrict__ x, int n, float z, float weight, float* __restrict__ loss,
+                  __nv_bfloat16* __restrict__ d_logits) {
+    float acc = 0.f;
+    const float wn = weight / (float)n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = x[i];
+        acc += fmaxf(v, 0.f) - v * z + log1pf(expf(-fabsf(v)));
+        if (d_logits) {
+            float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            f[0] = wn * (1.f / (1.f + expf(-v)) - z);
+            reinterpret_cast<uint4*>(d_logits)[i] = bf8_pack(f);
+        }
+    }
+    acc = warp_sum(acc);
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+        atomicAdd(loss, t * wn);
+    }
+}
+
+// =============================================================================================
+// TF-style Adam over one flat f32 buffer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps)
+// =============================================================================================
+__global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                               float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+                               float grad_scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+// per-channel sum over pixels of a bf16 [P,C] tensor (bias gradients of non-BN layers): out[c] += sum_p g[p,c]
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const __nv_bfloat16* __restrict__ g, long long P, int C, float* __restrict__ out) {
+    const int CG = C >> 3;
+    const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, lanes = blockDim.x / CG;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
+        float t[8];
+        bf8_unpack(*reinterpret_cast<const uint4*>(g + p * C + cg * 8), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += t[j];
+    }
+    __shared__ float red[256 * 8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = s[j];
+    __syncthreads();
+    if (pl == 0) {
+        for (int l = 1; l < lanes; ++l)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += red[(l * CG + cg) * 8 + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(out + cg * 8 + j, s[j]);
+    }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int ew_image_prep(const float* x, long long P, const float* a, const float* b, const int* perm, void* out, cudaStream_t st) {
+    ImgPrep q;
+    for (int c = 0; c < 3; ++c) { q.a[c] = a[c]; q.b[c] = b[c]; q.perm[c] = perm[c]; }
+    image_prep_kernel<<<grid_for(P, 256), 256, 0, st>>>(x, P, q, reinterpret_cast<__nv_bfloat16*>(out));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_image_prep_bwd(const void* g, long long P, const float* a, const int* perm, int accumulate, float* dx, cudaStream_t st) {
+    ImgPrep q;
+    for (int c = 0; c < 3; ++c) { q.a[c] = a[c]; q.b[c] = 0.f; q.perm[c] = perm[c]; }
+    image_prep_bwd_kernel<<<grid_for(P, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), P, q, accumulate, dx);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, int C,
+                   double count, float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean,
+                   float* srstd, cudaStream_t st) {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ssum, ssq, bias, gamma, beta, C, (float)count, eps, decay, mm, mv,
+                                                        scale, shift, smean, srstd);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
+                    void* out, cudaStream_t st) {
+    KP_REQUIRE(C % 8 == 0, "bn_act_apply: C=%d must be a multiple of 8", C);
+    const long long total = (long long)N * H * W * (C / 8) * (upsample ? 4 : 1);
+    const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (upsample) bn_act_apply_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(xi, scale, shift, relu, N, H, W, C, o);
+    else bn_act_apply_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(xi, scale, shift, relu, N, H, W, C, o);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
+                  const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
+                  void* dx, cudaStream_t st) {
+    KP_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_act_bwd: C=%d must be 8 x a power of two <= 2048", C);
+    const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dout);
+    const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+    KP_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
+    KP_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
+    const long long P = (long long)N * H * W;
+    const int lanes = 256 / (C / 8);
+    const int rgrid = grid_for((P + lanes - 1) / lanes, 1, 148 * 4);
+    if (upsample)
+        bn_act_bwd_reduce_kernel<true><<<rgrid, 256, 0, st>>>(d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma);
+    else
+        bn_act_bwd_reduce_kernel<false><<<rgrid, 256, 0, st>>>(d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma);
+    KP_LAUNCHED();
+    const long long total = P * (C / 8);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dx);
+    if (upsample)
+        bn_act_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
+    else
+        bn_act_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, cudaStream_t st) {
+    KP_REQUIRE(n_elems % 8 == 0, "act_mask_bwd: element count must be a multiple of 8");
+    act_mask_bwd_kernel<<<grid_for(n_elems / 8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                     reinterpret_cast<const __nv_bfloat16*>(y), alpha,
+                                                                     n_elems / 8, reinterpret_cast<__nv_bfloat16*>(g));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, cudaStream_t st) {
+    KP_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: needs C%%8==0 and even H,W");
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C,
+                                                             reinterpret_cast<__nv_bfloat16*>(out));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_maxpool_bwd(const void* dy, const void* x, int relu_mask, int N, int H, int W, int C, void* dx, cudaStream_t st) {
+    KP_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: needs C%%8==0 and even H,W");
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                             reinterpret_cast<const __nv_bfloat16*>(x), relu_mask, N, H, W, C,
+                                                             reinterpret_cast<__nv_bfloat16*>(dx));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_compose_fwd(const float* heads, const float* im, long long P, int clip, float* final_out, float* crude_out,
+                   float* mask_out, cudaStream_t st) {
+    compose_fwd_kernel<<<grid_for(P, 256), 256, 0, st>>>(heads, im, P, clip, final_out, crude_out, mask_out);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_compose_bwd(const float* d_final, const float* heads, const float* im, long long P, void* d_heads, cudaStream_t st) {
+    compose_bwd_kernel<<<grid_for(P, 256), 256, 0, st>>>(d_final, heads, im, P, reinterpret_cast<__nv_bfloat16*>(d_heads));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_pack_channels(const void* const* src, const int* C, const int* is_f32, int n, long long P, int Ctot, void* out,
+                     cudaStream_t st) {
+    KP_REQUIRE(n >= 1 && n <= 3, "pack_channels: 1..3 sources");
+    PackSrc s;
+    s.n = n;
+    int sum = 0;
+    for (int i = 0; i < 3; ++i) {
+        s.ptr[i] = i < n ? src[i] : nullptr;
+        s.C[i] = i < n ? C[i] : 0;
+        s.is_f32[i] = i < n ? is_f32[i] : 0;
+        sum += s.C[i];
+    }
+    KP_REQUIRE(sum <= Ctot, "pack_channels: sources (%d channels) exceed Ctot=%d", sum, Ctot);
+    pack_channels_kernel<<<grid_for(P * Ctot, 256), 256, 0, st>>>(s, P, Ctot, reinterpret_cast<__nv_bfloat16*>(out));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_unpack_channels(const void* g, long long P, int Ctot, void* const* dst, const int* C, const int* is_f32, int n,
+                       cudaStream_t st) {
+    KP_REQUIRE(n >= 1 && n <= 3, "unpack_channels: 1..3 destinations");
+    UnpackDst d;
+    d.n = n;
+    for (int i = 0; i < 3; ++i) {
+        d.ptr[i] = i < n ? dst[i] : nullptr;
+        d.C[i] = i < n ? C[i] : 0;
+        d.is_f32[i] = i < n ? is_f32[i] : 0;
+    }
+    unpack_channels_kernel<<<grid_for(P * Ctot, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), P, Ctot, d);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_l1_pair(const void* feat_gt, const void* feat_pred, long long half_elems, float weight, float* loss, void* d_pred,
+               cudaStream_t st) {
+    KP_REQUIRE(half_elems % 8 == 0, "l1_pair: element count must be a multiple of 8");
+    l1_pair_kernel<<<grid_for(half_elems / 8, 256, 148 * 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(feat_gt),
+                                                                           reinterpret_cast<const __nv_bfloat16*>(feat_pred),
+                                                                           half_elems / 8, weight / (float)half_elems, loss,
+                                                                           reinterpret_cast<__nv_bfloat16*>(d_pred));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_bce_logits(const float* x, int n, float z, float weight, float* loss, void* d_logits, cudaStream_t st) {
+    bce_logits_kernel<<<1, 256, 0, st>>>(x, n, z, weight, loss, reinterpret_cast<__nv_bfloat16*>(d_logits));
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int t,
+               float grad_scale, cudaStream_t st) {
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t));
+    adam_tf_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)lr_t, b1, b2, eps, grad_scale);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st) {
+    KP_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "channel_sum: C=%d must be 8 x a power of two", C);
+    const int lanes = 256 / (C / 8);
+    channel_sum_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g),
+                                                                                       P, C, out);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+
+}  // namespace kp

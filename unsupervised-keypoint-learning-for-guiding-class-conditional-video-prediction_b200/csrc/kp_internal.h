@@ -26,4 +26,32 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
 // conv_wgrad.cu
 int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
 
+// elementwise.cu
+int ew_image_prep(const float* x, long long P, const float* a, const float* b, const int* perm, void* out, cudaStream_t st);
+int ew_image_prep_bwd(const void* g, long long P, const float* a, const int* perm, int accumulate, float* dx, cudaStream_t st);
+int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, int C,
+                   double count, float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean,
+                   float* srstd, cudaStream_t st);
+int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
+                    void* out, cudaStream_t st);
+int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
+                  const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
+                  void* dx, cudaStream_t st);
+int ew_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, cudaStream_t st);
+int ew_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, cudaStream_t st);
+int ew_maxpool_bwd(const void* dy, const void* x, int relu_mask, int N, int H, int W, int C, void* dx, cudaStream_t st);
+int ew_compose_fwd(const float* heads, const float* im, long long P, int clip, float* final_out, float* crude_out,
+                   float* mask_out, cudaStream_t st);
+int ew_compose_bwd(const float* d_final, const float* heads, const float* im, long long P, void* d_heads, cudaStream_t st);
+int ew_pack_channels(const void* const* src, const int* C, const int* is_f32, int n, long long P, int Ctot, void* out,
+                     cudaStream_t st);
+int ew_unpack_channels(const void* g, long long P, int Ctot, void* const* dst, const int* C, const int* is_f32, int n,
+                       cudaStream_t st);
+int ew_l1_pair(const void* feat_gt, const void* feat_pred, long long half_elems, float weight, float* loss, void* d_pred,
+               cudaStream_t st);
+int ew_bce_logits(const float* x, int n, float z, float weight, float* loss, void* d_logits, cudaStream_t st);
+int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int t,
+               float grad_scale, cudaStream_t st);
+int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st);
+
 }  // namespace kp

@@ -1,0 +1,313 @@
+"""Execution engine of the stage-1 path: name-keyed parameter store, backward tape, convolution layers.
+
+This is host-side plumbing (buffers, launch order, gradient bookkeeping); every FLOP runs in
+libkp_b200.so.  Parameters use the TF variable names of the reference graph
+(`<scope>/conv2d/{kernel,bias}`, `<scope>/{gamma,beta,moving_mean,moving_variance}`; HWIO kernels) so a
+state dict can be exchanged with the oracle and, eventually, with reference checkpoints
+(models/base_model.py:74-92).
+"""
+import math
+
+import torch
+
+from . import conv as cv
+from . import ops
+from . import tapconv as tc
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+class ParamGroup:
+    """One flat f32 buffer (+ grad / Adam slots) holding many named tensors: a single Adam launch and a single
+    gradient all-reduce per optimiser step."""
+
+    def __init__(self, device, trainable=True):
+        self.device = device
+        self.trainable = trainable
+        self.specs = []          # (name, shape, offset)
+        self.index = {}
+        self.total = 0
+        self.data = self.grad = self.m = self.v = None
+
+    def add(self, name, shape):
+        assert self.data is None and name not in self.index
+        n = int(math.prod(shape))
+        self.index[name] = len(self.specs)
+        self.specs.append((name, tuple(shape), self.total))
+        self.total += (n + 3) // 4 * 4      # keep every tensor 16-byte aligned
+
+    def finalize(self):
+        self.data = torch.zeros(self.total, device=self.device, dtype=F32)
+        if self.trainable:
+            self.grad = torch.zeros_like(self.data)
+            self.m = torch.zeros_like(self.data)
+            self.v = torch.zeros_like(self.data)
+
+    def _view(self, buf, name):
+        _, shape, off = self.specs[self.index[name]]
+        return buf[off:off + int(math.prod(shape))].view(shape)
+
+    def __contains__(self, name):
+        return name in self.index
+
+    def p(self, name):
+        return self._view(self.data, name)
+
+    def g(self, name):
+        return self._view(self.grad, name)
+
+    def names(self):
+        return [s[0] for s in self.specs]
+
+
+class Tape:
+    """Reverse-mode tape: closures run in reverse; gradients of activations are keyed by tensor identity."""
+
+    def __init__(self):
+        self.ops = []
+        self.g = {}
+        self.keep = []
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    def grad(self, t):
+        return self.g.get(id(t))
+
+    def set_grad(self, t, g):
+        self.keep.append(t)
+        self.g[id(t)] = g
+
+    def acquire(self, t, dtype=None, shape=None):
+        """Gradient buffer of activation `t` and whether it already holds a gradient (=> accumulate)."""
+        k = id(t)
+        if k in self.g:
+            return self.g[k], True
+        buf = torch.empty(tuple(t.shape) if shape is None else shape, device=t.device, dtype=dtype or t.dtype)
+        self.keep.append(t)
+        self.g[k] = buf
+        return buf, False
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+        self.ops.clear()
+        self.g.clear()
+        self.keep.clear()
+
+
+class Context:
+    """Parameters + execution state shared by the network builders (the analogue of TF's default graph)."""
+
+    def __init__(self, device, n_pts=40):
+        self.device = torch.device(device)
+        self.n_pts = n_pts
+        self.G = ParamGroup(self.device)              # generator: image_encoder, pose_encoder, translator
+        self.D = ParamGroup(self.device)              # img_discr
+        self.S = ParamGroup(self.device, False)       # BN moving statistics
+        self.V = ParamGroup(self.device, False)       # VGG19 constants
+        self.version = 0                              # bumped whenever parameter values change
+        self.tape = None
+        self.update_moving = False
+        self.train_D = False                          # accumulate img_discr weight gradients
+        self.train_G = False
+        self._plans = {}
+        self._packed = {}
+
+    # ---- parameter lookup ----
+    def group_of(self, name):
+        for g in (self.G, self.D, self.S, self.V):
+            if name in g:
+                return g
+        raise KeyError(name)
+
+    def p(self, name):
+        return self.group_of(name).p(name)
+
+    def has(self, name):
+        return any(name in g for g in (self.G, self.D, self.S, self.V))
+
+    def params_changed(self):
+        self.version += 1
+        self._packed.clear()
+
+    def load_state_dict(self, sd):
+        """sd: name -> tensor/ndarray (HWIO kernels).  Unknown names are ignored, like BaseModel.restore."""
+        loaded = []
+        for name, val in sd.items():
+            if self.has(name):
+                self.p(name).copy_(torch.as_tensor(val).to(self.device, F32))
+                loaded.append(name)
+        self.params_changed()
+        return loaded
+
+    def state_dict(self):
+        out = {}
+        for g in (self.G, self.D, self.S, self.V):
+            for n in g.names():
+                out[n] = g.p(n).detach().clone()
+        return out
+
+    # ---- plan / packed-weight caches ----
+    def plan(self, kind, key, builder):
+        k = (kind,) + key
+        if k not in self._plans:
+            self._plans[k] = builder()
+        return self._plans[k]
+
+    def packed(self, key, builder):
+        if key not in self._packed:
+            self._packed[key] = builder()
+        return self._packed[key]
+
+
+# --------------------------------------------------------------------------------------------------
+# convolution layer (+ BN / activation), forward and tape entry
+# --------------------------------------------------------------------------------------------------
+def _conv_weights(ctx, wnames):
+    """HWIO kernel of the layer; several TF variables may be fused along Cout (translator heads)."""
+    if len(wnames) == 1:
+        return ctx.p(wnames[0])
+    return torch.cat([ctx.p(n) for n in wnames], dim=3)
+
+
+def _bias_vec(ctx, bnames, rows_pad):
+    if bnames is None:
+        return None
+    parts = [ctx.p(n) for n in bnames]
+    b = parts[0] if len(parts) == 1 else torch.cat(parts)
+    return cv.pad_vec(b, rows_pad)
+
+
+def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode=False, act=tc.ACT_NONE, alpha=0.0,
+               upsample=False, out_f32=False, need_input_grad=True, stats_prefix=None):
+    """layers.conv [+ layers.batch_norm + relu] [+ resize x2] of the reference, on bf16 NHWC tensors.
+
+    srcs: list of bf16 [N,H,W,C] tensors (virtual channel concat).  Returns the layer output (bf16, or f32 when
+    out_f32).  bn: BN scope name or None.  With bn and train_mode the batch statistics are used (and the
+    moving averages updated when ctx.update_moving); with bn and not train_mode BN is folded into the
+    convolution.  A tape entry is recorded when ctx.tape is set.
+    """
+    wnames = [wnames] if isinstance(wnames, str) else list(wnames)
+    if isinstance(bnames, str):
+        bnames = [bnames]
+    shapes = tuple(tuple(s.shape) for s in srcs)
+    w = _conv_weights(ctx, wnames)
+    cout = w.shape[3]
+    cin_src = sum(s[3] for s in shapes)
+    if cin_src > w.shape[2]:
+        # sources carry zero-padded channels (3-channel images stored as 16, the 208-channel joint embedding as 256)
+        w = torch.nn.functional.pad(w, (0, 0, 0, cin_src - w.shape[2]))
+    fplan, (N, Ho, Wo) = ctx.plan("fwd", (shapes, k, stride, pad, cout), lambda: tc.plan_conv_fwd(list(shapes), k, stride, pad, cout))
+    dev = ctx.device
+    group = ctx.group_of(wnames[0])
+    wkey = tuple(wnames)
+
+    if bn is not None and not train_mode:
+        # inference: fold BN (moving statistics) into the convolution, ReLU in the epilogue
+        def build():
+            scale = ctx.p(bn + "/gamma") * torch.rsqrt(ctx.p(bn + "/moving_variance") + 1e-5)
+            b = ctx.p(bnames[0]) if bnames else torch.zeros(cout, device=dev)
+            bias = (b - ctx.p(bn + "/moving_mean")) * scale + ctx.p(bn + "/beta")
+            return cv.pack_weights(fplan, w, row_scale=scale), cv.pad_vec(bias, fplan.rows_pad)
+        wp, bias = ctx.packed(("fold", wkey, shapes), build)
+        y = torch.empty((N, Ho, Wo, cout), device=dev, dtype=BF16)
+        cv.run_plan(fplan, srcs, wp, bias, y, act=tc.ACT_RELU)
+        if upsample:
+            y = ops.bn_act_apply(y, None, None, relu=False, upsample=True)
+        return y
+
+    wp = ctx.packed(("fwd", wkey, shapes), lambda: cv.pack_weights(fplan, w))
+    bias = ctx.packed(("bias", wkey, fplan.rows_pad), lambda: _bias_vec(ctx, bnames, fplan.rows_pad))
+
+    if bn is not None:
+        # training-mode BN: conv (+bias) with statistics in the epilogue -> finalize -> normalise + ReLU (+ x2)
+        ssum = torch.zeros(fplan.rows_pad, device=dev, dtype=F32)
+        ssq = torch.zeros(fplan.rows_pad, device=dev, dtype=F32)
+        y_pre = torch.empty((N, Ho, Wo, cout), device=dev, dtype=BF16)
+        cv.run_plan(fplan, srcs, wp, bias, y_pre, act=tc.ACT_NONE, stats=(ssum, ssq))
+        mm = ctx.p(bn + "/moving_mean") if ctx.update_moving else None
+        mv = ctx.p(bn + "/moving_variance") if ctx.update_moving else None
+        scale, shift, mean, rstd = ops.bn_finalize(ssum, ssq, bias, ctx.p(bn + "/gamma"), ctx.p(bn + "/beta"),
+                                                   N * Ho * Wo, mm, mv)
+        out = ops.bn_act_apply(y_pre, scale, shift, relu=True, upsample=upsample)
+        if ctx.tape is not None:
+            tape = ctx.tape
+
+            def bwd():
+                dout = tape.grad(out)
+                if dout is None:
+                    return
+                dy, dgamma, dbeta = ops.bn_act_bwd(dout, y_pre, scale, shift, mean, rstd, relu=True, upsample=upsample)
+                group.g(bn + "/gamma").add_(dgamma)
+                group.g(bn + "/beta").add_(dbeta)
+                _conv_backward(ctx, tape, srcs, shapes, wnames, None, w, k, stride, pad, cout, dy, group, need_input_grad)
+            tape.record(bwd)
+        return out
+
+    # plain conv + bias + activation in the epilogue
+    y = torch.empty((N, Ho, Wo, cout), device=dev, dtype=F32 if out_f32 else BF16)
+    cv.run_plan(fplan, srcs, wp, bias, y, act=act, alpha=alpha)
+    if ctx.tape is not None:
+        tape = ctx.tape
+
+        def bwd():
+            dy = tape.grad(y)          # bf16, channels padded to a multiple of 8 for f32-output layers
+            if dy is None:
+                return
+            if act == tc.ACT_RELU:
+                dy = ops.act_mask_bwd(dy, y, 0.0)
+            elif act == tc.ACT_LEAKY:
+                dy = ops.act_mask_bwd(dy, y, alpha)
+            _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad)
+        tape.record(bwd)
+    return y
+
+
+def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad):
+    """dy: bf16 gradient w.r.t. the convolution output, [N,Ho,Wo,cpad] with cpad = round_up(cout, 8)."""
+    cpad = dy.shape[3]
+    train = group.trainable and ((group is ctx.G and ctx.train_G) or (group is ctx.D and ctx.train_D))
+    cin = sum(s[3] for s in shapes)
+    if train:
+        cin_real = ctx.p(wnames[0]).shape[2]
+        direct = cpad == cout and len(wnames) == 1 and cin_real == cin
+        if direct:
+            gw = group.g(wnames[0])
+        else:
+            gw = torch.zeros((k, k, cin, cpad), device=ctx.device, dtype=F32)
+        c0 = 0
+        for s, shp in zip(srcs, shapes):
+            C = shp[3]
+            wplan = ctx.plan("wgrad", (shp, k, stride, pad, cpad, c0, cin),
+                             lambda shp=shp, c0=c0, C=C: tc.plan_conv_wgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
+            cv.run_wgrad(wplan, s, dy, gw)
+            c0 += C
+        if not direct:
+            o = 0
+            for n in wnames:
+                co = ctx.p(n).shape[3]
+                group.g(n).add_(gw[:, :, :cin_real, o:o + co])
+                o += co
+        if bnames:
+            gb = torch.zeros(cpad, device=ctx.device, dtype=F32)
+            ops.channel_sum(dy, gb)
+            o = 0
+            for n in bnames:
+                co = ctx.p(n).shape[0]
+                group.g(n).add_(gb[o:o + co])
+                o += co
+    if not need_input_grad:
+        return
+    wpad = w if cpad == cout else torch.nn.functional.pad(w, (0, cpad - cout))
+    c0 = 0
+    for s, shp in zip(srcs, shapes):
+        C = shp[3]
+        plans = ctx.plan("dgrad", (shp, k, stride, pad, cpad, c0, cin),
+                         lambda shp=shp, c0=c0, C=C: tc.plan_conv_dgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
+        dx, acc = tape.acquire(s)
+        for i, p in enumerate(plans):
+            wp = ctx.packed(("dgrad", tuple(wnames), shp, c0, cpad, i), lambda p=p: cv.pack_weights(p, wpad))
+            cv.run_plan(p, [dy], wp, None, dx, accumulate=acc)
+        c0 += C

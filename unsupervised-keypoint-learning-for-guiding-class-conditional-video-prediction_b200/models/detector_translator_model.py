@@ -1,0 +1,243 @@
+"""DetectorTranslatorModel — the stage-1 trainer of /root/reference/models/detector_translator_model.py on B200.
+
+Keeps the reference's surface (`build(inputs)`, `train_step`, `test_step`, `collect_test_results`, attribute
+names) and its step semantics:
+  * one train_step = a D run on one batch, then a G run on ANOTHER batch (each `sess.run` pulled a new batch);
+  * BN always uses batch statistics when is_training (also in test_step); moving averages are updated only in
+    the G run; the shared pose_encoder normalises each of its two calls separately;
+  * loss_D = BCE(D(real),1) + BCE(D(fake),0); loss_G = perceptual(VGG19, 5 taps, L1) + BCE(D(fake),1);
+  * lr = start * decay^(global_step/step) (continuous), two Adam(beta1=.5, beta2=.999, eps=1e-8) optimisers,
+    global_step += 1 in the G run.
+Data parallelism: one process per GPU; gradients of the flat G / D buffers are summed with one NCCL all-reduce
+each per step and scaled by 1/world_size inside the Adam kernel; BN statistics stay per replica.
+"""
+import time
+from datetime import datetime
+
+import torch
+
+from .. import engine as E
+from .. import networks
+from .. import ops
+from ..utils import model as model_utils
+from .base_model import BaseModel, GlobalStep, log
+
+
+class DetectorTranslatorModel(BaseModel):
+    name = 'detector_translator'
+
+    def __init__(self, config, global_step=None, is_training=True, device=None, seed=0, process_group=None):
+        super().__init__(is_training)
+        train_config = config['training']
+        model_config = config['model']
+        paths_config = config['paths']
+        self.lr = train_config['lr'] if self.is_training else None
+        self.batch_size = train_config['batch_size']
+        self.n_points = model_config['n_pts']
+        self.log_dir = paths_config['log_dir']
+        self.vgg19_path = paths_config.get('vggnet')
+        self.colors = model_utils.get_n_colors(model_config['n_pts'], pastel_factor=0.0)
+        self.global_step = global_step if global_step is not None else GlobalStep(0)
+        self.device = torch.device(device if device is not None else "cuda")
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.inputs = None
+        self.t_D = 0
+        self.t_G = 0
+        # outputs of the last forward pass (names follow the reference's attributes)
+        self.final_output = self.crude_output = self.mask = None
+        self.current_keypoints = self.future_keypoints = None
+        self.loss_D = self.loss_G = None
+        self.loss_D_real = self.loss_D_fake = self.loss_G_recon = self.loss_G_adv = None
+
+        self.ctx = E.Context(self.device, n_pts=self.n_points)
+        networks.build_parameters(self.ctx, self.n_points, with_vgg=True)
+        self._init_weights(seed)
+
+    # ------------------------------------------------------------------------------------------
+    def _init_weights(self, seed):
+        """xavier-uniform kernels, zero biases (tf.contrib.layers.xavier_initializer, layers.py:8); VGG19 weights
+        come from vgg19.npy when the file exists, otherwise He-normal random (benchmarks: there is no network)."""
+        import math
+        import os
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        ctx = self.ctx
+        for grp in (ctx.G, ctx.D):
+            for n in grp.names():
+                if n.endswith("/kernel"):
+                    p = grp.p(n)
+                    k1, k2, cin, cout = p.shape
+                    lim = math.sqrt(6.0 / (k1 * k2 * (cin + cout)))
+                    p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) * lim).to(self.device))
+        if self.vgg19_path and os.path.exists(self.vgg19_path):
+            networks.vgg.load_npy_into(ctx, self.vgg19_path)
+        else:
+            for n in ctx.V.names():
+                p = ctx.V.p(n)
+                if n.endswith("/filter"):
+                    p.copy_((torch.randn(p.shape, generator=g) * math.sqrt(2.0 / (9 * p.shape[2]))).to(self.device))
+                else:
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.05).to(self.device))
+        ctx.params_changed()
+
+    def _extra_state(self):
+        return {"global_step": int(self.global_step.value), "t_D": self.t_D, "t_G": self.t_G,
+                "adam": {"G_m": self.ctx.G.m.cpu(), "G_v": self.ctx.G.v.cpu(), "D_m": self.ctx.D.m.cpu(),
+                         "D_v": self.ctx.D.v.cpu()}}
+
+    def _load_extra_state(self, ex):
+        self.global_step.value = int(ex.get("global_step", 0))
+        self.t_D, self.t_G = int(ex.get("t_D", 0)), int(ex.get("t_G", 0))
+        if "adam" in ex:
+            self.ctx.G.m.copy_(ex["adam"]["G_m"]); self.ctx.G.v.copy_(ex["adam"]["G_v"])
+            self.ctx.D.m.copy_(ex["adam"]["D_m"]); self.ctx.D.v.copy_(ex["adam"]["D_v"])
+
+    # ------------------------------------------------------------------------------------------
+    def build(self, inputs):
+        """inputs: dict with 'image' and 'future_image' (float32 NHWC CUDA tensors in [-1,1]), or a callable
+        returning such a dict — called once per run, which reproduces the reference's "every sess.run pulls a
+        new batch" behaviour (train.py:46-50)."""
+        self.inputs = inputs
+        networks.set_context(self.ctx)
+
+    def _next_batch(self, feed_dict=None):
+        src = feed_dict if isinstance(feed_dict, dict) and 'image' in feed_dict else self.inputs
+        b = src() if callable(src) else src
+        return b['image'], b['future_image']
+
+    def _define_forward_pass(self, im, future_im, for_G_run=True):
+        """reference :160-184.  Returns the heads tensor too (crude+mask before compose)."""
+        networks.set_context(self.ctx)
+        tm = self.is_training
+        embeddings = networks.image_encoder(im, tm) if for_G_run else \
+            [im] + networks.encoder(networks._prep(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
+        current_gauss_pt, current_pt_map = networks.pose_encoder_with_maps(im, self.n_points, tm, (32, 32))
+        future_gauss_pt, future_pt_map = networks.pose_encoder_with_maps(future_im, self.n_points, tm, (32, 32))
+        joint_embedding = networks.joint_embedding(embeddings[-2], current_pt_map, future_pt_map)
+        heads = networks.translator_heads(joint_embedding, tm)
+        final_output = networks.compose(im, heads)
+        self.final_output = final_output
+        self.crude_output, self.mask = heads[..., :3], heads[..., 3:4]
+        self.current_keypoints, self.future_keypoints = current_gauss_pt, future_gauss_pt
+        return final_output
+
+    @property
+    def current_keypoints_map(self):
+        return model_utils.get_gaussian_maps(self.current_keypoints, [128, 128])
+
+    @property
+    def future_keypoints_map(self):
+        return model_utils.get_gaussian_maps(self.future_keypoints, [128, 128])
+
+    def _current_lr(self):
+        return self.lr['start_val'] * self.lr['decay'] ** (float(self.global_step.value) / self.lr['step'])
+
+    # ---- losses (reference :246-289) ----
+    def _compute_loss_D(self, future_im_pred, future_im, backward):
+        ctx = self.ctx
+        B = future_im.shape[0]
+        x = torch.cat([future_im, future_im_pred.detach()], dim=0)
+        logits = networks.img_discr(x)                       # [2B,6,6,1]: real half then fake half
+        loss = torch.zeros(2, device=self.device)
+        d_real = ops.bce_logits(logits[:B], 1.0, 1.0, loss[0:1], backward)
+        d_fake = ops.bce_logits(logits[B:], 0.0, 1.0, loss[1:2], backward)
+        if backward:
+            ctx.tape.set_grad(logits, torch.cat([d_real, d_fake], dim=0))
+        return loss
+
+    def _compute_loss_G(self, future_im_pred, future_im, backward):
+        ctx = self.ctx
+        loss = torch.zeros(2, device=self.device)             # [reconstruction, adversarial]
+        tape = ctx.tape
+        ctx.tape = None
+        feat_gt = networks.vgg.features_from_prepared(ops.image_prep(future_im, ops.VGG_PREP), need_input_grad=False)
+        ctx.tape = tape
+        xp = networks._prep_with_grad(ctx, future_im_pred, ops.VGG_PREP) if backward else ops.image_prep(future_im_pred, ops.VGG_PREP)
+        feat_pred = networks.vgg.features_from_prepared(xp, need_input_grad=backward)
+        for fg, fp in zip(feat_gt, feat_pred):
+            d = torch.empty_like(fp) if backward else None
+            ops.l1_pair(fg, fp, 1.0 / len(feat_pred), loss[0:1], d)
+            if backward:
+                tape.set_grad(fp, d)
+        fake_ = networks.img_discr(future_im_pred, need_input_grad=backward)
+        d_adv = ops.bce_logits(fake_, 1.0, 1.0, loss[1:2], backward)
+        if backward:
+            tape.set_grad(fake_, d_adv)
+        return loss
+
+    def _allreduce(self, buf):
+        if self.world > 1:
+            torch.distributed.all_reduce(buf, group=self.pg)
+
+    # ---- the two runs of one train step ----
+    def _run_D(self, im, future_im):
+        ctx = self.ctx
+        ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = None, False, False, False
+        fake = self._define_forward_pass(im, future_im, for_G_run=False)
+        ctx.tape, ctx.train_D = E.Tape(), True
+        ctx.D.grad.zero_()
+        loss = self._compute_loss_D(fake, future_im, backward=True)
+        ctx.tape.backward()
+        ctx.tape, ctx.train_D = None, False
+        self._allreduce(ctx.D.grad)
+        self.t_D += 1
+        ops.adam_tf(ctx.D.data, ctx.D.grad, ctx.D.m, ctx.D.v, self._current_lr(), self.t_D, grad_scale=1.0 / self.world)
+        ctx.params_changed()
+        return loss
+
+    def _run_G(self, im, future_im):
+        ctx = self.ctx
+        ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = E.Tape(), True, True, False
+        ctx.G.grad.zero_()
+        fake = self._define_forward_pass(im, future_im, for_G_run=True)
+        loss = self._compute_loss_G(fake, future_im, backward=True)
+        ctx.tape.backward()
+        ctx.tape, ctx.update_moving, ctx.train_G = None, False, False
+        self._allreduce(ctx.G.grad)
+        self.t_G += 1
+        ops.adam_tf(ctx.G.data, ctx.G.grad, ctx.G.m, ctx.G.v, self._current_lr(), self.t_G, grad_scale=1.0 / self.world)
+        self.global_step.value += 1
+        ctx.params_changed()
+        return loss
+
+    def train_step(self, sess=None, feed_dict=None, step=0, batch_size=None, should_write_log=False,
+                   should_write_summary=False):
+        start_time = time.time()
+        im, fut = self._next_batch(feed_dict)
+        loss_D = self._run_D(im, fut)
+        im, fut = self._next_batch(feed_dict)
+        loss_G = self._run_G(im, fut)
+        self._last_losses = (loss_D, loss_G)
+        if should_write_log:
+            ld, lg = float(loss_D.sum().item()), float(loss_G.sum().item())
+            duration = time.time() - start_time
+            bs = batch_size or im.shape[0]
+            log_format = '%s: step %d, loss_D = %.4f, loss_G = %.4f (%.1f examples/sec) %.3f sec/batch'
+            log.info(log_format % (datetime.now(), step, ld, lg, bs / float(duration), duration))
+            self.loss_D, self.loss_G = ld, lg
+
+    def test_step(self, sess=None, feed_dict=None, step=0, test_idx=0, batch_size=None):
+        ctx = self.ctx
+        start_time = time.time()
+        im, fut = self._next_batch(feed_dict)
+        ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = None, False, False, False
+        fake = self._define_forward_pass(im, fut, for_G_run=False)
+        lD = self._compute_loss_D(fake, fut, backward=False)
+        lG = self._compute_loss_G(fake, fut, backward=False)
+        vals = torch.cat([lD, lG]).tolist()
+        duration = time.time() - start_time
+        self.loss_D_real, self.loss_D_fake, self.loss_G_recon, self.loss_G_adv = vals
+        return vals[0] + vals[1], vals[2] + vals[3], duration, batch_size or im.shape[0]
+
+    def collect_test_results(self, results, step):
+        average_loss_D = sum(x[0] for x in results) / len(results)
+        average_loss_G = sum(x[1] for x in results) / len(results)
+        total_duration = sum(x[2] for x in results)
+        average_duration = total_duration / len(results)
+        num_examples = sum(x[3] for x in results)
+        log_format = 'test: %s: step %d, loss_D = %.4f, loss_G = %.4f (%.1f examples/sec) %.3f sec/batch'
+        log.info(log_format % (datetime.now(), step, average_loss_D, average_loss_G, num_examples / total_duration,
+                               average_duration))
+        return average_loss_D, average_loss_G

@@ -1,0 +1,160 @@
+"""Thin torch-facing wrappers of the memory-bound C-ABI entry points (include/kp_b200.h).  No arithmetic here."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f3(v):
+    return (ctypes.c_float * 3)(*[float(x) for x in v])
+
+
+def _i3(v):
+    return (ctypes.c_int * 3)(*[int(x) for x in v])
+
+
+IDENT_PREP = ((1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (0, 1, 2))
+# (x+1)/2*255 then RGB->BGR minus VGG_MEAN (detector_translator_model.py:262-263, vgg.py:15-19)
+VGG_MEAN = (103.939, 116.779, 123.68)
+VGG_PREP = ((127.5, 127.5, 127.5), tuple(127.5 - m for m in VGG_MEAN), (2, 1, 0))
+
+
+def image_prep(x, prep=IDENT_PREP):
+    """f32 [..., 3] -> bf16 [..., 16]."""
+    assert x.dtype == F32 and x.shape[-1] == 3 and x.is_cuda
+    x = x.contiguous()
+    out = torch.empty(tuple(x.shape[:-1]) + (16,), device=x.device, dtype=BF16)
+    a, b, perm = prep
+    _lib.call("kp_image_prep", _p(x), x.numel() // 3, _f3(a), _f3(b), _i3(perm), _p(out), _st())
+    return out
+
+
+def image_prep_bwd(g, dx, prep=IDENT_PREP, accumulate=False):
+    a, _, perm = prep
+    _lib.call("kp_image_prep_bwd", _p(g), g.numel() // 16, _f3(a), _i3(perm), 1 if accumulate else 0, _p(dx), _st())
+    return dx
+
+
+def bn_finalize(ssum, ssq, bias, gamma, beta, count, moving_mean, moving_var, eps=1e-5, decay=0.999):
+    C = gamma.shape[0]
+    dev = gamma.device
+    scale = torch.empty(C, device=dev, dtype=F32)
+    shift = torch.empty(C, device=dev, dtype=F32)
+    mean = torch.empty(C, device=dev, dtype=F32)
+    rstd = torch.empty(C, device=dev, dtype=F32)
+    _lib.call("kp_bn_finalize", _p(ssum), _p(ssq), _p(bias), _p(gamma), _p(beta), C, float(count), eps, decay,
+              _p(moving_mean), _p(moving_var), _p(scale), _p(shift), _p(mean), _p(rstd), _st())
+    return scale, shift, mean, rstd
+
+
+def bn_act_apply(x, scale, shift, relu=True, upsample=False):
+    N, H, W, C = x.shape
+    out = torch.empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C), device=x.device, dtype=BF16)
+    _lib.call("kp_bn_act_apply", _p(x), _p(scale), _p(shift), 1 if relu else 0, 1 if upsample else 0, N, H, W, C, _p(out),
+              _st())
+    return out
+
+
+def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False):
+    N, H, W, C = x.shape
+    dbeta = torch.empty(C, device=x.device, dtype=F32)
+    dgamma = torch.empty(C, device=x.device, dtype=F32)
+    dx = torch.empty_like(x)
+    _lib.call("kp_bn_act_bwd", _p(dout), _p(x), _p(scale), _p(shift), _p(mean), _p(rstd), 1 if relu else 0,
+              1 if upsample else 0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _st())
+    return dx, dgamma, dbeta
+
+
+def act_mask_bwd(dy, y, alpha):
+    g = torch.empty_like(y)
+    _lib.call("kp_act_mask_bwd", _p(dy), _p(y), float(alpha), y.numel(), _p(g), _st())
+    return g
+
+
+def maxpool_fwd(x):
+    N, H, W, C = x.shape
+    out = torch.empty((N, H // 2, W // 2, C), device=x.device, dtype=BF16)
+    _lib.call("kp_maxpool2x2_fwd", _p(x), N, H, W, C, _p(out), _st())
+    return out
+
+
+def maxpool_bwd(dy, x, dx, relu_mask=False, accumulate=False):
+    N, H, W, C = x.shape
+    _lib.call("kp_maxpool2x2_bwd", _p(dy), _p(x), (1 if relu_mask else 0) | (2 if accumulate else 0), N, H, W, C, _p(dx),
+              _st())
+    return dx
+
+
+def compose_fwd(heads, im, clip=False, want_parts=False):
+    P = im.numel() // 3
+    final = torch.empty_like(im)
+    crude = torch.empty_like(im) if want_parts else None
+    mask = torch.empty(tuple(im.shape[:-1]) + (1,), device=im.device, dtype=F32) if want_parts else None
+    _lib.call("kp_mask_compose_fwd", _p(heads), _p(im), P, 1 if clip else 0, _p(final), _p(crude), _p(mask), _st())
+    return final, crude, mask
+
+
+def compose_bwd(d_final, heads, im):
+    P = im.numel() // 3
+    out = torch.empty(tuple(im.shape[:-1]) + (8,), device=im.device, dtype=BF16)
+    _lib.call("kp_mask_compose_bwd", _p(d_final), _p(heads), _p(im), P, _p(out), _st())
+    return out
+
+
+def pack_channels(srcs, Ctot):
+    """cat(srcs, -1) cast to bf16, zero padded to Ctot channels."""
+    n = len(srcs)
+    srcs = [s.contiguous() for s in srcs]
+    P = srcs[0].numel() // srcs[0].shape[-1]
+    out = torch.empty(tuple(srcs[0].shape[:-1]) + (Ctot,), device=srcs[0].device, dtype=BF16)
+    ptrs = (ctypes.c_void_p * 3)(*[s.data_ptr() for s in srcs], *([None] * (3 - n)))
+    Cs = (ctypes.c_int * 3)(*[s.shape[-1] for s in srcs], *([0] * (3 - n)))
+    f32 = (ctypes.c_int * 3)(*[1 if s.dtype == F32 else 0 for s in srcs], *([0] * (3 - n)))
+    _lib.call("kp_pack_channels", ptrs, Cs, f32, n, P, Ctot, _p(out), _st())
+    return out
+
+
+def unpack_channels(g, dsts):
+    n = len(dsts)
+    Ctot = g.shape[-1]
+    P = g.numel() // Ctot
+    ptrs = (ctypes.c_void_p * 3)(*[d.data_ptr() for d in dsts], *([None] * (3 - n)))
+    Cs = (ctypes.c_int * 3)(*[d.shape[-1] for d in dsts], *([0] * (3 - n)))
+    f32 = (ctypes.c_int * 3)(*[1 if d.dtype == F32 else 0 for d in dsts], *([0] * (3 - n)))
+    _lib.call("kp_unpack_channels", _p(g), P, Ctot, ptrs, Cs, f32, n, _st())
+    return dsts
+
+
+def l1_pair(feat_gt, feat_pred, weight, loss, d_pred):
+    _lib.call("kp_l1_pair_fwd_bwd", _p(feat_gt), _p(feat_pred), feat_pred.numel(), float(weight), _p(loss), _p(d_pred),
+              _st())
+
+
+def bce_logits(logits, label, weight, loss, want_grad):
+    n = logits.numel()
+    d = torch.empty(tuple(logits.shape[:-1]) + (8,), device=logits.device, dtype=BF16) if want_grad else None
+    _lib.call("kp_bce_logits_fwd_bwd", _p(logits), n, float(label), float(weight), _p(loss), _p(d), _st())
+    return d
+
+
+def adam_tf(p, g, m, v, lr, t, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    _lib.call("kp_adam_tf", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), beta1, beta2, eps, int(t), float(grad_scale),
+              _st())
+
+
+def channel_sum(g, out):
+    C = g.shape[-1]
+    _lib.call("kp_channel_sum", _p(g), g.numel() // C, C, _p(out), _st())
+    return out

@@ -33,6 +33,7 @@ class TapConvDesc(ctypes.Structure):
                 ("out_off", ctypes.c_longlong), ("out_sw", ctypes.c_longlong), ("out_sh", ctypes.c_longlong),
                 ("out_sn", ctypes.c_longlong),
                 ("Cout", ctypes.c_int), ("out_f32", ctypes.c_int), ("act", ctypes.c_int), ("alpha", ctypes.c_float),
+                ("accumulate", ctypes.c_int),
                 ("TW", ctypes.c_int), ("TH", ctypes.c_int), ("TN", ctypes.c_int), ("BN", ctypes.c_int)]
 
 
@@ -74,7 +75,7 @@ class TapPlan:
         first = self.taps[0][2]
         return sum(-(-self.views[first + s]["C"] // self.CB) for s in range(self.n_src))
 
-    def desc(self, act=ACT_NONE, alpha=0.0, out_f32=False, cout_written=None, tile=None, bn=0):
+    def desc(self, act=ACT_NONE, alpha=0.0, out_f32=False, cout_written=None, tile=None, bn=0, accumulate=False):
         d = TapConvDesc()
         d.N = self.N
         d.n_maps = len(self.views)
@@ -91,6 +92,7 @@ class TapPlan:
         d.Cout = self.rows if cout_written is None else cout_written
         d.out_f32 = 1 if out_f32 else 0
         d.act, d.alpha = act, alpha
+        d.accumulate = 1 if accumulate else 0
         if tile is not None:
             d.TW, d.TH, d.TN = tile
         d.BN = bn
