@@ -168,7 +168,9 @@ class Ctx:
         return y
 
     def cbr(self, x, conv_scope, bn_scope, train_mode, stride=1):
-        return torch.relu(self.bn(self.conv(x, conv_scope, stride), bn_scope, train_mode))
+        y = torch.relu(self.bn(self.conv(x, conv_scope, stride), bn_scope, train_mode))
+        self.taps[conv_scope] = y
+        return y
 
 
 def encoder(ctx, x, train_mode, prefix):

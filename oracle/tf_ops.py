@@ -33,7 +33,7 @@ def conv2d(x, kernel, bias=None, stride=1, pad=0):
     pt, pb = same_pad(xc.shape[2], k, stride)
     pl, pr = same_pad(xc.shape[3], k, stride)
     xc = F.pad(xc, (pl, pr, pt, pb))
-    y = F.conv2d(xc, kernel.permute(3, 2, 0, 1), bias, stride=stride)
+    y = F.conv2d(xc, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=stride)
     return y.permute(0, 2, 3, 1)
 
 

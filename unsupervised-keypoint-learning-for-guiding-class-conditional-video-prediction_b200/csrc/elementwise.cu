@@ -554,9 +554,10 @@ __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const __nv_bfloat16* __restrict__ g, long long P, int C, float* __restrict__ out) {
     const int CG = C >> 3;
-    const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, lanes = blockDim.x / CG;
+    const int lanes = blockDim.x / CG;                       // threads beyond lanes*CG idle (C/8 need not divide 256)
+    const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
+    for (long long p = (long long)blockIdx.x * lanes + pl; pl < lanes && p < P; p += (long long)gridDim.x * lanes) {
         float t[8];
         bf8_unpack(*reinterpret_cast<const uint4*>(g + p * C + cg * 8), t);
 #pragma unroll
@@ -728,7 +729,7 @@ int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float 
     return KP_OK;
 }
 int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st) {
-    KP_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "channel_sum: C=%d must be 8 x a power of two", C);
+    KP_REQUIRE(C % 8 == 0 && C / 8 <= 256, "channel_sum: C=%d must be a multiple of 8, at most 2048", C);
     const int lanes = 256 / (C / 8);
     channel_sum_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g),
                                                                                        P, C, out);

@@ -112,6 +112,7 @@ class Context:
         self.update_moving = False
         self.train_D = False                          # accumulate img_discr weight gradients
         self.train_G = False
+        self.debug = None                             # dict: layer scope -> internals (tests / probes only)
         self._plans = {}
         self._packed = {}
 
@@ -232,6 +233,8 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
         scale, shift, mean, rstd = ops.bn_finalize(ssum, ssq, bias, ctx.p(bn + "/gamma"), ctx.p(bn + "/beta"),
                                                    N * Ho * Wo, mm, mv)
         out = ops.bn_act_apply(y_pre, scale, shift, relu=True, upsample=upsample)
+        if ctx.debug is not None:
+            ctx.debug[wnames[0].replace("/conv2d/kernel", "")] = (out, y_pre, scale, shift, mean, rstd, upsample)
         if ctx.tape is not None:
             tape = ctx.tape
 
