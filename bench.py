@@ -1,12 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — stage-1 hot-path benchmark (contract in the task statement / DESIGN.md §Measurement).
+"""bench.py — stage-1 hot-path benchmark (contract: task statement; details in DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload k1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|k1] [--impl ours|reference]
 
-Prints ONE JSON line (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input.
-Workloads:
-  k1   BASELINE.json configs[1]: fused soft-argmax + Gaussian render, 1024 frames x 40 keypoints,
-       fp32 logits [1024,128,128,40] ~ N(0,5^2) per GPU (frames shard across GPUs, no collective).
+Prints ONE JSON line (rank 0).
+Workloads
+  train  BASELINE.json configs[2] — the configuration the metric "stage-1 frames/sec at 1/2/4/8 B200" is quoted on:
+         one reference `train_step` (D run on one batch + G run on another, fwd+bwd incl. VGG19 perceptual loss,
+         two Adam updates) at batch 32 per GPU, random-init weights incl. VGG19, synthetic frames 128x128,
+         40 keypoints, frame-batch data parallel with one NCCL all-reduce per optimiser.  A step consumes
+         4*32 frames per GPU (2 batches x (image, future_image)).
+  k1     BASELINE.json configs[1] — fused soft-argmax + Gaussian render micro-bench, 1024 frames per GPU.
+The default run measures `train` and appends the k1 roofline as `"k1": {...}` (a few extra seconds).
 """
 import argparse
 import json
@@ -20,7 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-K1_BYTES_PER_FRAME = 128 * 128 * 40 * 4 + 32 * 32 * 40 * 4 + 40 * 2 * 4  # 2 785 600
+K1_BYTES_PER_FRAME = 128 * 128 * 40 * 4 + 32 * 32 * 40 * 4 + 40 * 2 * 4   # 2 785 600
+TRAIN_GFLOP_PER_EXAMPLE = 152.369                                          # SURVEY.md §8d config 3 (useful conv work)
+CONFIG = {"paths": {"data_dir": "", "vggnet": None, "log_dir": "/tmp/kp_b200_logs"},
+          "training": {"batch_size": 32, "lr": {"start_val": 1e-4, "step": 20000, "decay": 0.95}},
+          "model": {"n_pts": 40, "n_action": 9, "cell_info": [1024, 1024], "vae_dim": 64}}
 
 
 def _peaks():
@@ -37,12 +46,8 @@ class ClockSampler:
     """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML, 20 ms period)."""
 
     def __init__(self, index):
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
-        self._stop = threading.Event()
-        self._thr = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop, self._thr = threading.Event(), None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -54,13 +59,8 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
-        names = {
-            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
-        }
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80}
         while not self._stop.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
@@ -82,12 +82,11 @@ class ClockSampler:
             self._stop.set()
             self._thr.join(timeout=2)
         med = int(statistics.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (numpy restatement of utils/model.py) on the host cores
+# CPU arms: the oracle (torch-CPU / numpy restatement of the reference) on the host cores
 # --------------------------------------------------------------------------------------------------
 def _cpu_k1_chunk(args):
     import numpy as np
@@ -97,12 +96,11 @@ def _cpu_k1_chunk(args):
     x = (rng.standard_normal((n, 128, 128, 40), dtype=np.float32) * np.float32(5.0))
     t0 = time.perf_counter()
     mu, px, py, maps = o.softargmax_render_fwd(x, [32, 32])
-    dt = time.perf_counter() - t0
-    return dt, float(mu.sum())
+    return time.perf_counter() - t0, float(mu.sum())
 
 
 def cpu_k1(frames_per_worker, workers, reps):
-    """Frames/s of the oracle over `workers` processes, each doing `frames_per_worker` frames, best of `reps`."""
+    """frames/s of the numpy oracle of utils/model.py over `workers` processes."""
     import multiprocessing as mp
     best = None
     if workers <= 1:
@@ -110,8 +108,7 @@ def cpu_k1(frames_per_worker, workers, reps):
             dt, _ = _cpu_k1_chunk((r, frames_per_worker))
             best = dt if best is None else min(best, dt)
         return frames_per_worker / best
-    ctx = mp.get_context("fork")
-    with ctx.Pool(workers) as pool:
+    with mp.get_context("fork").Pool(workers) as pool:
         for r in range(reps):
             res = pool.map(_cpu_k1_chunk, [(r * workers + i, frames_per_worker) for i in range(workers)])
             dt = max(d for d, _ in res)
@@ -119,190 +116,343 @@ def cpu_k1(frames_per_worker, workers, reps):
     return frames_per_worker * workers / best
 
 
+class CpuTrainer:
+    """The reference train_step restated on torch CPU (oracle/networks.py): D run + G run with autograd + TF Adam."""
+
+    def __init__(self, batch, seed=0):
+        import numpy as np
+        import torch
+        from oracle import networks as ON
+        self.torch, self.ON, self.B = torch, ON, batch
+        self.P = ON.init_params(seed, dtype=torch.float32)
+        rng = np.random.default_rng(seed)
+        self.batches = [tuple(torch.from_numpy(rng.uniform(-1, 1, (batch, 128, 128, 3)).astype(np.float32)) for _ in range(2))
+                        for _ in range(2)]
+        self.state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in self.P.items()
+                      if not k.startswith("vgg") and "moving" not in k}
+        self.t = 0
+
+    def _apply(self, names, lr):
+        from oracle import tf_ops as T
+        torch = self.torch
+        with torch.no_grad():
+            for n in names:
+                p = self.P[n]
+                if p.grad is None:
+                    continue
+                m, v = self.state[n]
+                newp, m, v = T.adam_tf(p.detach(), p.grad, m, v, self.t, lr)
+                self.state[n] = (m, v)
+                self.P[n] = newp
+
+    def step(self):
+        torch, ON = self.torch, self.ON
+        self.t += 1
+        d_names = [k for k in self.state if "img_discr" in k]
+        g_names = [k for k in self.state if "img_discr" not in k]
+        # D run
+        im, fut = self.batches[0]
+        for k in self.P:
+            self.P[k] = self.P[k].detach().requires_grad_(k in d_names)
+        ctx = ON.Ctx(self.P)
+        with torch.no_grad():
+            out = ON.forward_pass(ctx, im, fut, 40, True)
+        lD = ON.loss_D(ctx, out["final_output"], fut)[0]
+        lD.backward()
+        self._apply(d_names, 1e-4)
+        # G run
+        im, fut = self.batches[1]
+        for k in self.P:
+            self.P[k] = self.P[k].detach().requires_grad_(k in g_names)
+        ctx = ON.Ctx(self.P)
+        out = ON.forward_pass(ctx, im, fut, 40, True)
+        lG = ON.loss_G(ctx, out["final_output"], fut)[0]
+        lG.backward()
+        self._apply(g_names, 1e-4)
+        with torch.no_grad():
+            for name, val in ctx.updates:
+                self.P[name] = val.detach()
+        return float(lD), float(lG)
+
+
+def cpu_train(batch, steps, warmup=1):
+    """frames/s (4*batch frames per step) of the torch-CPU oracle train step, median over `steps`."""
+    import torch
+    tr = CpuTrainer(batch)
+    for _ in range(warmup):
+        tr.step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.step()
+        ts.append(time.perf_counter() - t0)
+    return 4 * batch / statistics.median(ts), torch.get_num_threads(), statistics.median(ts)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; TF 1.12 cannot be installed here)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU path.  TensorFlow 1.12 cannot be installed here, so this is the oracle
+    port of the same step (torch CPU, all host threads), on a bounded sample of the workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 32))
-    frames_per_worker = 8
-    vals = []
-    t_all = time.perf_counter()
-    for _ in range(max(args.warmup, 1)):
-        cpu_k1(frames_per_worker, workers, 1)
-    for _ in range(args.steps):
-        vals.append(cpu_k1(frames_per_worker, workers, 1))
-        if time.perf_counter() - t_all > 150:
-            break
-    v = statistics.median(vals)
-    sample = "%d steps x %d frames (%d procs x %d), numpy fp32 oracle of utils/model.py" % (
-        len(vals), frames_per_worker * workers, workers, frames_per_worker)
-    line = {
-        "impl": "reference", "metric": "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "value": v,
-        "unit": "frames/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-        "ms_per_step": 1e3 * frames_per_worker * workers / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "k1: fused soft-argmax + render, frames [128,128,40] fp32 -> mu + maps [32,32,40]",
-                   "frames_per_step": frames_per_worker * workers},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": workers, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
+    if args.workload == "k1":
+        workers = max(1, min(os.cpu_count() or 1, 32))
+        vals = [cpu_k1(8, workers, 1) for _ in range(max(args.warmup, 1) + min(args.steps, 10))][max(args.warmup, 1):]
+        v, cores = statistics.median(vals), workers
+        sample = "%d steps x %d frames (%d procs), numpy fp32 oracle of utils/model.py" % (len(vals), 8 * workers, workers)
+        metric, wl, steps, ms = "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "k1", len(vals), 1e3 * 8 * workers / v
+    else:
+        b = args.cpu_batch
+        steps = max(1, min(args.steps, args.cpu_steps))
+        v, cores, sec = cpu_train(b, steps, warmup=1)
+        sample = ("%d train_steps (D run + G run, fwd+bwd incl. VGG19, TF Adam) at batch %d instead of 32: torch-CPU fp32 "
+                  "oracle of the reference graph, %d threads" % (steps, b, cores))
+        metric, wl, ms = "stage-1 frames/sec (train_step: D run + G run)", "train", sec * 1e3
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": wl, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
 # --------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arms
 # --------------------------------------------------------------------------------------------------
-def run_ours(args):
+def _dist_setup():
     import torch
     import torch.distributed as dist
-    import __graft_entry__ as g
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
-        g.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist.barrier()
     else:
         torch.cuda.set_device(0)
-    import kp_b200
-    from kp_b200 import k1
-    lib = kp_b200._lib.load()
-    dev = torch.device("cuda", local_rank if world > 1 else 0)
-    peaks = _peaks()
+        local_rank = 0
+    return world, rank, local_rank
 
+
+def _barrier(world):
+    import torch
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(x, world, dev):
+    import torch
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_k1(args, world, rank, dev, lib):
+    import torch
+    from kp_b200 import k1
     B = args.frames
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     logits = torch.randn((B, 128, 128, 40), device=dev, generator=gen) * 5.0   # 2.68 GB >> 126 MB L2
-    torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        k1.softargmax_render_fwd(logits, (32, 32), want_prob=False)
+    _barrier(world)
+    steps = args.k1_steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.kp_launch_count()
+    ev0.record()
+    for _ in range(steps):
+        k1.softargmax_render_fwd(logits, (32, 32), want_prob=False)
+    ev1.record()
+    _barrier(world)
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world, dev) / steps
+    del logits
+    peaks = _peaks()
+    achieved = K1_BYTES_PER_FRAME * B / (ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    return {"workload": "BASELINE configs[1]: fused soft-argmax + Gaussian render, %d frames/GPU [128,128,40] fp32 -> "
+                        "mu [40,2] + maps [32,32,40]; input 2.68 GB per launch >> 126 MB L2" % B,
+            "frames_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+            "gpu_launches": int(lib.kp_launch_count() - n0),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
+                         "kernel": "kp::k1_fwd_fast<5,8>", "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * B}}
 
-    def step():
-        return k1.softargmax_render_fwd(logits, (32, 32), want_prob=False)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+def run_ours(args):
+    import torch
+    import __graft_entry__ as g
+    world, rank, local_rank = _dist_setup()
+    if rank == 0:
+        g.build()
+    _barrier(world)
+    import kp_b200
+    from kp_b200 import models
+    lib = kp_b200._lib.load()
+    dev = torch.device("cuda", local_rank)
+    peaks = _peaks()
 
+    if args.workload == "k1":
+        r = bench_k1(args, world, rank, dev, lib)
+        if rank == 0:
+            print(json.dumps({"metric": "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "value": r["frames_per_s"],
+                              "unit": "frames/s", "n_gpus": world, "steps": r["steps"], "warmup": args.warmup,
+                              "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"]},
+                              "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]}))
+        return
+
+    # ------------------------------ train workload ------------------------------
+    B = args.batch
+    cfg = json.loads(json.dumps(CONFIG))
+    cfg["training"]["batch_size"] = B
+    model = models.DetectorTranslatorModel(cfg, is_training=True, device=dev, seed=0)
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    pool = [{"image": torch.rand((B, 128, 128, 3), device=dev, generator=gen) * 2 - 1,
+             "future_image": torch.rand((B, 128, 128, 3), device=dev, generator=gen) * 2 - 1} for _ in range(6)]
+    cursor = {"i": 0}
+
+    def feed():
+        cursor["i"] += 1
+        return pool[cursor["i"] % len(pool)]
+    model.build(feed)
+    launches_per_step = None
+    if not args.no_graph:
+        n0 = lib.kp_launch_count()
+        model.enable_cuda_graph(B)
+        launches_per_step = int(lib.kp_launch_count() - n0) // 2       # warm-up step + captured step
     for _ in range(args.warmup):
-        step()
-    barrier()
+        model.train_step()
+    _barrier(world)
     sampler = ClockSampler(dev.index or 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = lib.kp_launch_count()
     sampler.start()
-    barrier()
+    _barrier(world)
     ev0.record()
     for _ in range(args.steps):
-        out = step()
+        model.train_step()
     ev1.record()
-    barrier()
+    _barrier(world)
     clocks = sampler.stop()
-    launches = int(lib.kp_launch_count() - n0)
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    if launches_per_step is None:
+        launches_per_step = int(lib.kp_launch_count() - n0) // args.steps
+    ms_per_step = _max_over_ranks(ev0.elapsed_time(ev1), world, dev) / args.steps
+    frames_per_step = 4 * B                                              # 2 batches x (image, future_image)
+    value = world * frames_per_step / (ms_per_step * 1e-3)
+    lD, lG = model._last_losses
+    losses = [float(lD.sum().item()), float(lG.sum().item())]
 
-    # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
-    Bh = args.e2e_frames
-    host_in = torch.empty((Bh, 128, 128, 40), dtype=torch.float32, pin_memory=True)
-    host_in.normal_(0, 5.0)
-    host_mu = torch.empty((Bh, 40, 2), dtype=torch.float32, pin_memory=True)
-    host_maps = torch.empty((Bh, 32, 32, 40), dtype=torch.float32, pin_memory=True)
-    chunk = 64
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    dbuf = [torch.empty((chunk, 128, 128, 40), device=dev) for _ in range(2)]
+    # ---- end to end: pinned host frames -> H2D -> train_step -> loss D2H, every step ----
+    host = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in pool[:4]]
+    hcur = {"i": 0}
 
-    def e2e_step():
-        from kp_b200 import model_utils
-        for i, c0 in enumerate(range(0, Bh, chunk)):
-            s = streams[i & 1]
-            n = min(chunk, Bh - c0)
-            with torch.cuda.stream(s):
-                d = dbuf[i & 1][:n]
-                d.copy_(host_in[c0:c0 + n], non_blocking=True)
-                mu, maps = model_utils.soft_argmax_and_maps(d, [32, 32])
-                host_mu[c0:c0 + n].copy_(mu, non_blocking=True)
-                host_maps[c0:c0 + n].copy_(maps, non_blocking=True)
-        for s in streams:
-            s.synchronize()
-
-    e2e_steps = max(3, min(args.steps, 10))
+    def feed_host():
+        hcur["i"] += 1
+        hb = host[hcur["i"] % len(host)]
+        return {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+    model.build(feed_host)
+    e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
-        e2e_step()
-    barrier()
+        model.train_step()
+    _barrier(world)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Bh * e2e_steps / float(te.item())
+        model.train_step()
+        lD, lG = model._last_losses
+        _ = torch.cat([lD, lG]).cpu()                                    # the step's result crosses back every step
+    _barrier(world)
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, world, dev)
+    e2e_value = world * frames_per_step * e2e_steps / e2e_s
+    model.build(feed)
+
+    # ---- conv-kernel-only tensor throughput: one eager step with CUDA events around every conv launch ----
+    kern = None
+    if rank == 0 and not args.no_kernel_profile:
+        from kp_b200 import conv as cv
+        cv.PROFILE = []
+        saved = model._graph
+        model._graph = None
+        model.train_step()
+        torch.cuda.synchronize()
+        model._graph = saved
+        tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in cv.PROFILE)
+        tot_fl = sum(f for _, f, _, _ in cv.PROFILE)
+        by = {}
+        for kind, f, e0, e1 in cv.PROFILE:
+            a = by.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += f; a[1] += e0.elapsed_time(e1); a[2] += 1
+        kern = {"conv_launches": len(cv.PROFILE), "conv_ms": tot_ms, "conv_tflops": tot_fl / (tot_ms * 1e-3) / 1e12,
+                "by_kind": {k: {"launches": v[2], "ms": v[1], "tflops": v[0] / (v[1] * 1e-3) / 1e12} for k, v in by.items()}}
+        cv.PROFILE = None
+
+    k1r = None if args.no_k1 else bench_k1(args, world, rank, dev, lib)
 
     if rank == 0:
-        achieved = K1_BYTES_PER_FRAME * B / (ms_per_step * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+        step_tflops = TRAIN_GFLOP_PER_EXAMPLE * B / (ms_per_step * 1e-3) / 1e3
+        peak = peaks["bf16_tflops_sustained"]
+        achieved = kern["conv_tflops"] if kern else step_tflops
         cpu = None
-        if world == 1 or rank == 0:
-            try:
-                v = cpu_k1(args.cpu_frames, 1, 2)
-                cpu = {"value": v, "unit": "frames/s", "cores": 1, "kind": "port",
-                       "sample": "%d frames, best of 2, numpy fp32 oracle of utils/model.py (1 process), host has %d cores"
-                                 % (args.cpu_frames, os.cpu_count() or 0)}
-            except Exception as e:  # the baseline is reporting only; never fail the bench on it
-                cpu = {"value": None, "unit": "frames/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+        try:
+            v, cores, sec = cpu_train(args.cpu_batch, 1, warmup=0)
+            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "1 train_step at batch %d (%.1f s): torch-CPU fp32 oracle of the reference graph, %d threads, host "
+                             "has %d cores" % (args.cpu_batch, sec, cores, os.cpu_count() or 0)}
+        except Exception as e:   # reporting only
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         line = {
-            "metric": "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "k1: BASELINE configs[1] fused soft-argmax + render, %d frames/GPU "
-                                   "[128,128,40] fp32 -> mu [40,2] + maps [32,32,40]" % B,
-                       "frames_per_gpu": B, "n_pts": 40, "image_hw": [128, 128], "map_hw": [32, 32],
-                       "l2": "input 2.68 GB per step >> 126 MB L2 (no flush needed)", "parallelism": "frames sharded, no collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
-                         "kernel": "k1_fwd_fast<5,8>", "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * B},
+            "metric": "stage-1 frames/sec (train_step: D run + G run)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: stage-1 detector_translator train_step (D run + G run on different "
+                                   "batches, fwd+bwd incl. VGG19 perceptual loss + img_discr, 2x Adam), random-init incl. VGG19",
+                       "batch_per_gpu": B, "frames_per_step_per_gpu": frames_per_step, "image_hw": [128, 128], "n_pts": 40,
+                       "examples_per_s": world * B / (ms_per_step * 1e-3), "parallelism": "dp%d" % world,
+                       "cuda_graph": not args.no_graph,
+                       "l2": "per-step working set (activations + 51 M parameters + Adam slots, several GB) >> 126 MB L2; "
+                             "6 input batches rotate",
+                       "losses_last_step": losses},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peaks["source"] + " (sustained: kernels timed inside a long step)",
+                         "kernel": "kp::tapconv_kernel / kp::wgrad_kernel (all conv launches of one step, CUDA events per launch)",
+                         "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peak,
+                         "algorithmic_flops_per_step": TRAIN_GFLOP_PER_EXAMPLE * B * 1e9, "kernels": kern},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Bh * 128 * 128 * 40 * 4,
-                    "d2h_bytes_per_step": Bh * (40 * 2 + 32 * 32 * 40) * 4, "frames_per_step": Bh, "steps": e2e_steps,
-                    "note": "pinned host logits -> H2D -> fused kernel -> D2H mu+maps, 2-stream chunked pipeline"},
-            "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 4 * B * 128 * 128 * 3 * 4,
+                    "d2h_bytes_per_step": 16, "steps": e2e_steps,
+                    "note": "pinned host frames -> H2D -> DetectorTranslatorModel.train_step -> losses D2H, every step"},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
         }
+        if k1r is not None:
+            line["k1"] = k1r
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="k1", choices=["k1"])
+    ap.add_argument("--workload", default="train", choices=["train", "k1"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=512)
-    ap.add_argument("--cpu-frames", type=int, default=48)
+    ap.add_argument("--batch", type=int, default=32, help="train: pairs per GPU per run")
+    ap.add_argument("--frames", type=int, default=1024, help="k1: frames per GPU per launch")
+    ap.add_argument("--k1-steps", type=int, default=100)
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-k1", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -216,9 +216,10 @@ int kp_l1_pair_fwd_bwd(const void* feat_gt, const void* feat_pred, long long n_e
  * *loss += weight*mean(...); d_logits (nullable) bf16 [n,8], channel 0 = weight/n*(sigmoid(x)-label). */
 int kp_bce_logits_fwd_bwd(const float* logits, int n, float label, float weight, float* loss, void* d_logits, void* stream);
 /* tf.train.AdamOptimizer update over one flat buffer (models/detector_translator_model.py:198-202):
- * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t); p -= lr_t*m/(sqrt(v)+eps); grads are multiplied by grad_scale first. */
+ * lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t); p -= lr_t*m/(sqrt(v)+eps); grads are multiplied by grad_scale first.
+ * lr_t_dev (nullable): device scalar holding a precomputed lr_t that overrides lr/t (CUDA-graph replays).     */
 int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-               int t, float grad_scale, void* stream);
+               int t, float grad_scale, const float* lr_t_dev, void* stream);
 /* out[c] += sum over pixels of g bf16 [P,C] (bias gradients). */
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream);
 

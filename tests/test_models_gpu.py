@@ -1,0 +1,149 @@
+"""GPU: the model classes (reference surface) end to end: losses and inference outputs against the oracle, training
+step semantics, CUDA-graph replay against eager execution, FinalModel output structure."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"paths": {"data_dir": "", "vggnet": None, "log_dir": "/tmp/kp_b200_test"},
+       "training": {"batch_size": 4, "lr": {"start_val": 1e-4, "step": 20000, "decay": 0.95}},
+       "model": {"n_pts": 40, "n_action": 9, "cell_info": [1024, 1024], "vae_dim": 64}}
+
+
+def _data(B, seed=0):
+    rng = np.random.default_rng(seed)
+    im = torch.from_numpy(rng.uniform(-1, 1, (B, 128, 128, 3)).astype(np.float32))
+    fut = torch.from_numpy(rng.uniform(-1, 1, (B, 128, 128, 3)).astype(np.float32))
+    return im, fut
+
+
+def _oracle_params():
+    from oracle import networks as ON
+    P = ON.init_params(0, dtype=torch.float32, bias_scale=0.02)
+    return ON.randomize_bn(P, 1)
+
+
+def test_losses_and_inference_forward_match_oracle(cuda_dev):
+    from kp_b200 import models
+    from oracle import networks as ON
+    P = _oracle_params()
+    im, fut = _data(4)
+    model = models.DetectorTranslatorModel(CFG, is_training=True, device=cuda_dev)
+    model.ctx.load_state_dict(P)
+    model.build({"image": im.to(cuda_dev), "future_image": fut.to(cuda_dev)})
+    lD, lG, _, bs = model.test_step()
+    assert bs == 4
+    octx = ON.Ctx({k: v.clone() for k, v in P.items()})
+    ref = ON.forward_pass(octx, im, fut, 40, True)
+    rD, rDr, rDf = [float(x) for x in ON.loss_D(octx, ref["final_output"], fut)]
+    rG, rGr, rGa = [float(x) for x in ON.loss_G(octx, ref["final_output"], fut)]
+    assert abs(lD - rD) <= 2e-3 * rD and abs(lG - rG) <= 1e-2 * rG
+    assert abs(model.loss_G_recon - rGr) <= 1e-2 * rGr and abs(model.loss_G_adv - rGa) <= 5e-3 * rGa
+    # inference mode (moving statistics, BN folded into the tcgen05 convs): bf16 end to end vs fp32 oracle
+    model.is_training = False
+    final = model._define_forward_pass(im.to(cuda_dev), fut.to(cuda_dev))
+    octx2 = ON.Ctx({k: v.clone() for k, v in P.items()})
+    ref_i = ON.forward_pass(octx2, im, fut, 40, False)
+    err = (final.cpu() - ref_i["final_output"]).norm() / ref_i["final_output"].norm()
+    assert err.item() <= 1e-2
+    assert (model.current_keypoints.cpu() - ref_i["current_pt"]).abs().max().item() <= 1e-4
+    assert (model.mask.cpu() - ref_i["mask"]).abs().max().item() <= 1e-2
+
+
+def test_train_step_semantics(cuda_dev):
+    """D run then G run on different batches; global_step += 1 per step; moving averages move only in the G run;
+    the dead image_encoder conv_7/conv_8 never receive a gradient; D weights change in the D run only."""
+    from kp_b200 import models
+    model = models.DetectorTranslatorModel(CFG, is_training=True, device=cuda_dev)
+    calls = []
+    im, fut = _data(4)
+    batch = {"image": im.to(cuda_dev), "future_image": fut.to(cuda_dev)}
+
+    def feed():
+        calls.append(1)
+        return batch
+    model.build(feed)
+    ctx = model.ctx
+    mm0 = ctx.S.data.clone()
+    d0, g0 = ctx.D.data.clone(), ctx.G.data.clone()
+    lossD = model._run_D(*model._next_batch())
+    assert torch.equal(ctx.S.data, mm0) and torch.equal(ctx.G.data, g0) and not torch.equal(ctx.D.data, d0)
+    d1 = ctx.D.data.clone()
+    lossG = model._run_G(*model._next_batch())
+    assert torch.equal(ctx.D.data, d1) and not torch.equal(ctx.G.data, g0) and not torch.equal(ctx.S.data, mm0)
+    assert int(model.global_step.value) == 1 and len(calls) == 2
+    assert torch.isfinite(lossD).all() and torch.isfinite(lossG).all()
+    dead = ctx.G.g("image_encoder/encoder/conv_8/conv2d/kernel")
+    assert dead.abs().max().item() == 0.0
+    assert ctx.G.g("image_encoder/encoder/conv_6/conv2d/kernel").abs().max().item() > 0.0
+    assert ctx.G.g("pose_encoder/encoder/conv_1/conv2d/kernel").abs().max().item() > 0.0
+    # first Adam step moves every touched weight by ~lr (TF bias correction), so |delta| <= lr * 1.001
+    delta = (ctx.D.data - d0).abs().max().item()
+    assert 0.5e-4 <= delta <= 1.001e-4
+    model.train_step()
+    assert int(model.global_step.value) == 2 and model.t_D == 2 and model.t_G == 2
+
+
+def test_cuda_graph_replay_matches_eager(cuda_dev):
+    from kp_b200 import models
+    B = 2
+    batches = [dict(zip(("image", "future_image"), [t.to(cuda_dev) for t in _data(B, s)])) for s in range(4)]
+
+    def make():
+        m = models.DetectorTranslatorModel(CFG, is_training=True, device=cuda_dev, seed=3)
+        cur = {"i": -1}
+
+        def feed():
+            cur["i"] += 1
+            return batches[cur["i"] % 4]
+        m.build(feed)
+        return m
+    eager, graph = make(), make()
+    graph.enable_cuda_graph(B)
+    assert torch.equal(eager.ctx.G.data, graph.ctx.G.data) and int(graph.global_step.value) == 0
+    for _ in range(2):
+        eager.train_step()
+        graph.train_step()
+    torch.cuda.synchronize()
+    assert int(graph.global_step.value) == 2 and graph.t_G == 2
+    le = torch.cat(eager._last_losses).cpu()
+    lg = torch.cat(graph._last_losses).cpu()
+    assert torch.allclose(le, lg, rtol=2e-2, atol=1e-3), (le, lg)
+    # Adam's first steps are sign-like (|step| ~ lr): compare the parameter change statistically
+    for grp_e, grp_g in ((eager.ctx.G, graph.ctx.G), (eager.ctx.D, graph.ctx.D)):
+        diff = (grp_e.data - grp_g.data).abs()
+        assert diff.max().item() <= 4.1e-4            # at most 2 steps x 2 replicas x lr apart
+        assert diff.mean().item() <= 2e-5             # and the overwhelming majority identical to rounding
+
+
+def test_final_model_outputs(cuda_dev):
+    from kp_b200 import models
+    from oracle import networks as ON
+    from oracle import k1_torch
+    P = _oracle_params()
+    fm = models.FinalModel(CFG, device=cuda_dev)
+    fm.ctx.load_state_dict(P)
+    rng = np.random.default_rng(5)
+    B = 2
+    im = torch.from_numpy(rng.uniform(-1, 1, (B, 128, 128, 3)).astype(np.float32))
+    seq = torch.from_numpy(rng.uniform(-0.9, 0.9, (B, 32, 40, 2)).astype(np.float32))
+    fm.build({"image": im.to(cuda_dev), "pred_seq": seq.to(cuda_dev), "real_im_seq": None, "action_code": None, "real_seq": None})
+    out = fm.run()
+    assert out["pred_im_seq"].shape == (B, 32, 128, 128, 3) and out["mask"].shape == (B, 32, 128, 128, 1)
+    assert out["pred_im_crude"].shape == (B, 32, 128, 128, 3) and out["current_points"].shape == (B, 128, 128, 3)
+    assert out["future_points"].shape == (B, 32, 128, 128, 3) and out["fut_pt_raw"].shape == (B, 32, 40, 2)
+    assert out["pred_im_seq"].abs().max().item() <= 1.0 and out["pred_im_crude"].abs().max().item() <= 1.0
+    # oracle for the first video, frame 7 (reference final_model.py:57-99, inference BN)
+    octx = ON.Ctx(P)
+    emb = ON.image_encoder(octx, im[:1], False)[-2]
+    first = ON.pose_encoder(octx, im[:1], 40, False)
+    cur = k1_torch.get_gaussian_maps(first, [32, 32])
+    fut = k1_torch.get_gaussian_maps(seq[0, 7:8], [32, 32])
+    crude, mask = ON.translator(octx, torch.cat([emb, cur, fut], dim=-1), False)
+    final = (im[:1] * mask + crude * (1 - mask)).clamp(-1, 1)
+    got = out["pred_im_seq"][0, 7].cpu()
+    assert ((got - final[0]).norm() / final.norm()).item() <= 1e-2
+    with pytest.raises(NotImplementedError):
+        fm.build({"image": im.to(cuda_dev)})
+        fm.run()

@@ -16,6 +16,27 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# bench.py sets PROFILE = [] to time every conv launch with CUDA events: entries (kind, algorithmic_flops, ev0, ev1).
+# Algorithmic = real channels only: plans of layers whose sources carry zero-padded channels have flop_scale < 1.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+
+
 def pack_weights(plan, w, row_scale=None, dtype=torch.bfloat16):
     """HWIO float kernel [k,k,Cin,Cout] -> packed [rows_pad, Ktot] bf16 (K-major) following plan.pack.
 
@@ -24,8 +45,10 @@ def pack_weights(plan, w, row_scale=None, dtype=torch.bfloat16):
     """
     k1, k2, cin, cout = w.shape
     CB = plan.CB
-    taps = torch.as_tensor(plan.pack["taps"], device=w.device, dtype=torch.long)
-    w3 = w.reshape(k1 * k2, cin, cout).index_select(0, taps)
+    w3 = w.reshape(k1 * k2, cin, cout)
+    if list(plan.pack["taps"]) != list(range(k1 * k2)):     # stride-2 dgrad parity classes use a subset of the taps
+        taps = torch.as_tensor(plan.pack["taps"], device=w.device, dtype=torch.long)
+        w3 = w3.index_select(0, taps)
     if plan.pack["mode"] == "fwd":
         if row_scale is not None:
             w3 = w3 * row_scale.view(1, 1, cout)
@@ -83,7 +106,10 @@ def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None
         ssum, ssq = stats
         if ssum.dtype != torch.float32 or ssum.shape[0] != plan.rows_pad or ssq.shape[0] != plan.rows_pad:
             raise ValueError("stats buffers must be f32 [rows_pad]")
-    with torch.cuda.device(out.device):
+    first = plan.taps[0][2]
+    k_real = len(plan.taps) * sum(plan.views[first + s]["C"] for s in range(plan.n_src))
+    flops = 2.0 * plan.N * plan.Ho * plan.Wo * k_real * plan.rows * getattr(plan, "flop_scale", 1.0)
+    with torch.cuda.device(out.device), _Timed("dgrad" if plan.pack["mode"] == "dgrad" else "fwd", flops):
         _lib.call("kp_tapconv_bf16", ctypes.byref(d), ptrs, wpacked.data_ptr(),
                   None if bias is None else bias.data_ptr(), out.data_ptr(),
                   None if ssum is None else ssum.data_ptr(), None if ssq is None else ssq.data_ptr(), _stream())
@@ -98,6 +124,7 @@ def run_wgrad(plan, x, dy, dw, splits=0):
     if not (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous()):
         raise ValueError("dW must be a contiguous f32 CUDA tensor (HWIO)")
     d = plan.desc(splits)
-    with torch.cuda.device(dw.device):
+    flops = 2.0 * plan.N * plan.Ho * plan.Wo * len(plan.taps) * plan.Cin * plan.Cout * getattr(plan, "flop_scale", 1.0)
+    with torch.cuda.device(dw.device), _Timed("wgrad", flops):
         _lib.call("kp_tapconv_wgrad_bf16", ctypes.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream())
     return dw

@@ -16,6 +16,7 @@
 #include "kp_internal.h"
 #include <cudaTypedefs.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace kp {
 
@@ -352,6 +353,10 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     KP_REQUIRE(TW * TH * TN == 128, "kp_tapconv: tile %dx%dx%d is not 128 pixels", TW, TH, TN);
     if (BN <= 0) {
         BN = d->Cout_pad <= 256 ? d->Cout_pad : (d->Cout_pad % 256 == 0 ? 256 : 128);
+        if (const char* e = getenv("KP_TAPCONV_BN_MAX")) {   // experiments: cap the channel tile
+            const int cap = atoi(e);
+            if (cap >= 16 && cap % 16 == 0 && BN > cap && d->Cout_pad % cap == 0) BN = cap;
+        }
     }
     KP_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && d->Cout_pad % BN == 0,
                "kp_tapconv: BN=%d must be a multiple of 16 in [16,256] dividing Cout_pad=%d", BN, d->Cout_pad);
@@ -405,7 +410,13 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.a_bytes = 128u * CB * 2u;
     p.b_bytes = (uint32_t)BN * CB * 2u;
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
-    int stages = (int)((200u * 1024u) / p.stage_bytes);
+    // Shared-memory budget per CTA.  The kernel is not persistent, so prologue / main loop / epilogue of different
+    // tiles only overlap when several CTAs share an SM: small tiles get a shallow ring (3 CTAs/SM), medium ones 2
+    // CTAs/SM, and only the 256-wide tiles take the whole SM (KP_TAPCONV_SMEM_KB overrides, for experiments).
+    uint32_t budget = p.stage_bytes <= 24u * 1024u ? 72u * 1024u : p.stage_bytes <= 32u * 1024u ? 100u * 1024u : 200u * 1024u;
+    if (const char* e = getenv("KP_TAPCONV_SMEM_KB")) budget = (uint32_t)atoi(e) * 1024u;
+    int stages = (int)(budget / p.stage_bytes);
+    if (stages < 2) stages = 2;
     if (stages > 8) stages = 8;
     if (stages > total_iters) stages = total_iters;
     if (stages < 1) stages = 1;

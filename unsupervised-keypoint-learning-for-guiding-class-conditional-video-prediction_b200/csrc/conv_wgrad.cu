@@ -13,7 +13,8 @@
 
 namespace kp {
 
-static constexpr int WG_KP = 64;  // pixels per pipeline stage (GEMM-K 64 = 4 UMMA K-steps)
+// pixels per pipeline stage: chosen so that every TMA box [KP pixels][CB channels] is 8 KB (KP = 64 / 128 / 256)
+static inline int wg_kp(int CB) { return 4096 / CB; }
 
 struct alignas(64) WgradKParams {
     CUtensorMap mapX[KP_MAX_MAPS];
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     constexpr uint32_t SBO = 8 * ROW_BYTES;
     constexpr uint32_t LAYOUT = (CB == 64) ? 2u : (CB == 32) ? 4u : 6u;
     constexpr uint32_t KSTEP_BYTES = 16 * ROW_BYTES;  // 16 pixels per UMMA K-step
+    constexpr int KP = 4096 / CB;                     // pixels per stage
 
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                 const uint32_t a_addr = smem_base + (uint32_t)st * p.stage_bytes;
                 const uint32_t b_addr = a_addr + p.a_bytes;
 #pragma unroll
-                for (int kk = 0; kk < WG_KP / 16; ++kk) {
+                for (int kk = 0; kk < KP / 16; ++kk) {
                     const uint64_t da = umma_smem_desc(a_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
                     const uint64_t db = umma_smem_desc(b_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
                     umma_bf16(tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
@@ -143,7 +145,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     WgradKParams p;
     memset(&p, 0, sizeof(p));
     const int CB = d->CB;
-    choose_pixel_tile(WG_KP, d->Wo, d->Ho, d->N, &p.TW, &p.TH, &p.TN);
+    choose_pixel_tile(wg_kp(CB), d->Wo, d->Ho, d->N, &p.TW, &p.TH, &p.TN);
     for (int m = 0; m < d->n_maps; ++m) {
         const int rc = encode_view_map(&p.mapX[m], d->map[m], x, d->N, CB, p.TW, p.TH, p.TN, "kp_wgrad X map");
         if (rc != KP_OK) return rc;
@@ -167,22 +169,27 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     int tm = 32;
     while (tm < p.BN) tm <<= 1;
     p.tmem_cols = tm;
-    p.box_bytes = (uint32_t)WG_KP * CB * 2u;
-    p.a_bytes = (uint32_t)(128 / CB) * p.box_bytes;                       // 16 KB
+    p.box_bytes = (uint32_t)wg_kp(CB) * CB * 2u;                          // 8 KB
+    // A region holds only the channel chunks that exist (the MMA still reads 128 rows = 128/CB chunks at LBO
+    // stride: the rows past the loaded chunks alias the B region / next stage / the slack below and produce
+    // accumulator rows that are never stored)
+    const int n_a_max = ((d->Cin < 128 ? d->Cin : 128) + CB - 1) / CB;
+    p.a_bytes = (uint32_t)n_a_max * p.box_bytes;
     const uint32_t b_bytes = (uint32_t)((p.BN + CB - 1) / CB) * p.box_bytes;
     p.stage_bytes = (p.a_bytes + b_bytes + 1023u) & ~1023u;
     int splits = d->splits;
     const int base_ctas = ci_blocks * p.co_blocks * d->n_taps;
     if (splits <= 0) {
-        splits = (2 * 148 + base_ctas - 1) / base_ctas;
-        const int max_by_work = (p.total_tiles + 3) / 4;   // at least ~4 pixel tiles per CTA
+        splits = (3 * 148 + base_ctas - 1) / base_ctas;
+        const int max_by_work = (p.total_tiles + 7) / 8;   // at least ~8 pixel tiles per CTA
         if (splits > max_by_work) splits = max_by_work;
     }
     if (splits < 1) splits = 1;
     if (splits > p.total_tiles) splits = p.total_tiles;
     p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
     splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-    int stages = (int)((160u * 1024u) / p.stage_bytes);
+    int stages = (int)((96u * 1024u) / p.stage_bytes);       // ~2 CTAs per SM
+    if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
     if (stages > p.tiles_per_split) stages = p.tiles_per_split;
     if (stages < 1) stages = 1;
@@ -190,7 +197,9 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     p.dw_out = dw;
     p.dw_off = d->dw_off; p.dw_stap = d->dw_stap; p.dw_sci = d->dw_sci;
 
-    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    const uint32_t over_read = (uint32_t)(128 / CB) * p.box_bytes;
+    const size_t slack = over_read > p.stage_bytes ? over_read - p.stage_bytes : 0;
+    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024 + slack;
     dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)d->n_taps, (unsigned)splits);
 #define KP_LAUNCH_WGRAD(CBV)                                                                                     \
     do {                                                                                                         \

@@ -538,8 +538,10 @@ bce_logits_kernel(const float* __restrict__ x, int n, float z, float weight, flo
 // TF-style Adam over one flat f32 buffer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps)
 // =============================================================================================
 __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                               float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
-                               float grad_scale) {
+                               float* __restrict__ v, long long n, float lr_t_host, const float* __restrict__ lr_t_dev,
+                               float b1, float b2, float eps, float grad_scale) {
+    // lr_t from device memory when given: lets a captured CUDA graph be replayed with a new step size
+    const float lr_t = lr_t_dev != nullptr ? *lr_t_dev : lr_t_host;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gi = g[i] * grad_scale;
         const float mi = m[i] + (gi - m[i]) * (1.f - b1);
@@ -722,9 +724,9 @@ int ew_bce_logits(const float* x, int n, float z, float weight, float* loss, voi
     return KP_OK;
 }
 int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int t,
-               float grad_scale, cudaStream_t st) {
+               float grad_scale, const float* lr_t_dev, cudaStream_t st) {
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t));
-    adam_tf_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)lr_t, b1, b2, eps, grad_scale);
+    adam_tf_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, g, m, v, n, (float)lr_t, lr_t_dev, b1, b2, eps, grad_scale);
     KP_LAUNCHED();
     return KP_OK;
 }

@@ -106,12 +106,12 @@ int kp_bce_logits_fwd_bwd(const float* logits, int n, float label, float weight,
     return ew_bce_logits(logits, n, label, weight, loss, d_logits, ST);
 }
 int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-               int t, float grad_scale, void* stream) {
+               int t, float grad_scale, const float* lr_t_dev, void* stream) {
     KP_NONNEG(n);
     if (n == 0) return KP_OK;
     KP_REQUIRE(t >= 1, "%s: step t must be >= 1", __func__);
     KP_NONNULL(p); KP_NONNULL(g); KP_NONNULL(m); KP_NONNULL(v);
-    return ew_adam_tf(p, g, m, v, n, lr, beta1, beta2, eps, t, grad_scale, ST);
+    return ew_adam_tf(p, g, m, v, n, lr, beta1, beta2, eps, t, grad_scale, lr_t_dev, ST);
 }
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream) {
     KP_NONNEG(P);

@@ -51,7 +51,7 @@ int ew_l1_pair(const void* feat_gt, const void* feat_pred, long long half_elems,
                cudaStream_t st);
 int ew_bce_logits(const float* x, int n, float z, float weight, float* loss, void* d_logits, cudaStream_t st);
 int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int t,
-               float grad_scale, cudaStream_t st);
+               float grad_scale, const float* lr_t_dev, cudaStream_t st);
 int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st);
 
 }  // namespace kp

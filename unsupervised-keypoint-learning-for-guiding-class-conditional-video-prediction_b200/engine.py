@@ -129,9 +129,14 @@ class Context:
     def has(self, name):
         return any(name in g for g in (self.G, self.D, self.S, self.V))
 
-    def params_changed(self):
+    def params_changed(self, group=None):
+        """Invalidate packed-weight caches: all of them, or only those built from `group`'s variables."""
         self.version += 1
-        self._packed.clear()
+        if group is None:
+            self._packed.clear()
+            return
+        for key in [k for k in self._packed if isinstance(k[1], tuple) and k[1] and k[1][0] in group]:
+            del self._packed[key]
 
     def load_state_dict(self, sd):
         """sd: name -> tensor/ndarray (HWIO kernels).  Unknown names are ignored, like BaseModel.restore."""
@@ -197,10 +202,12 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
     w = _conv_weights(ctx, wnames)
     cout = w.shape[3]
     cin_src = sum(s[3] for s in shapes)
+    flop_scale = w.shape[2] / float(cin_src)      # algorithmic-FLOP accounting ignores zero-padded channels
     if cin_src > w.shape[2]:
         # sources carry zero-padded channels (3-channel images stored as 16, the 208-channel joint embedding as 256)
         w = torch.nn.functional.pad(w, (0, 0, 0, cin_src - w.shape[2]))
     fplan, (N, Ho, Wo) = ctx.plan("fwd", (shapes, k, stride, pad, cout), lambda: tc.plan_conv_fwd(list(shapes), k, stride, pad, cout))
+    fplan.flop_scale = flop_scale
     dev = ctx.device
     group = ctx.group_of(wnames[0])
     wkey = tuple(wnames)
@@ -285,6 +292,7 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
             C = shp[3]
             wplan = ctx.plan("wgrad", (shp, k, stride, pad, cpad, c0, cin),
                              lambda shp=shp, c0=c0, C=C: tc.plan_conv_wgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
+            wplan.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
             cv.run_wgrad(wplan, s, dy, gw)
             c0 += C
         if not direct:
@@ -311,6 +319,7 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
                          lambda shp=shp, c0=c0, C=C: tc.plan_conv_dgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
         dx, acc = tape.acquire(s)
         for i, p in enumerate(plans):
+            p.flop_scale = (ctx.p(wnames[0]).shape[2] / float(cin)) * (cout / float(cpad))
             wp = ctx.packed(("dgrad", tuple(wnames), shp, c0, cpad, i), lambda p=p: cv.pack_weights(p, wpad))
             cv.run_plan(p, [dy], wp, None, dx, accumulate=acc)
         c0 += C

@@ -16,6 +16,7 @@ from datetime import datetime
 
 import torch
 
+from .. import dp
 from .. import engine as E
 from .. import networks
 from .. import ops
@@ -46,6 +47,9 @@ class DetectorTranslatorModel(BaseModel):
         self.inputs = None
         self.t_D = 0
         self.t_G = 0
+        self._graph = None
+        self._lr_dev = None
+        self._static = None
         # outputs of the last forward pass (names follow the reference's attributes)
         self.final_output = self.crude_output = self.mask = None
         self.current_keypoints = self.future_keypoints = None
@@ -55,6 +59,8 @@ class DetectorTranslatorModel(BaseModel):
         self.ctx = E.Context(self.device, n_pts=self.n_points)
         networks.build_parameters(self.ctx, self.n_points, with_vgg=True)
         self._init_weights(seed)
+        if self.world > 1:
+            dp.broadcast_parameters(self.ctx, 0, self.pg)      # replicas start (and stay) identical
 
     # ------------------------------------------------------------------------------------------
     def _init_weights(self, seed):
@@ -169,7 +175,7 @@ class DetectorTranslatorModel(BaseModel):
 
     def _allreduce(self, buf):
         if self.world > 1:
-            torch.distributed.all_reduce(buf, group=self.pg)
+            dp.allreduce_sum_(buf, self.pg)
 
     # ---- the two runs of one train step ----
     def _run_D(self, im, future_im):
@@ -183,8 +189,9 @@ class DetectorTranslatorModel(BaseModel):
         ctx.tape, ctx.train_D = None, False
         self._allreduce(ctx.D.grad)
         self.t_D += 1
-        ops.adam_tf(ctx.D.data, ctx.D.grad, ctx.D.m, ctx.D.v, self._current_lr(), self.t_D, grad_scale=1.0 / self.world)
-        ctx.params_changed()
+        ops.adam_tf(ctx.D.data, ctx.D.grad, ctx.D.m, ctx.D.v, self._current_lr(), self.t_D, grad_scale=1.0 / self.world,
+                    lr_t_dev=self._lr_dev[0:1] if self._lr_dev is not None else None)
+        ctx.params_changed(ctx.D)
         return loss
 
     def _run_G(self, im, future_im):
@@ -197,18 +204,69 @@ class DetectorTranslatorModel(BaseModel):
         ctx.tape, ctx.update_moving, ctx.train_G = None, False, False
         self._allreduce(ctx.G.grad)
         self.t_G += 1
-        ops.adam_tf(ctx.G.data, ctx.G.grad, ctx.G.m, ctx.G.v, self._current_lr(), self.t_G, grad_scale=1.0 / self.world)
+        ops.adam_tf(ctx.G.data, ctx.G.grad, ctx.G.m, ctx.G.v, self._current_lr(), self.t_G, grad_scale=1.0 / self.world,
+                    lr_t_dev=self._lr_dev[1:2] if self._lr_dev is not None else None)
         self.global_step.value += 1
-        ctx.params_changed()
+        ctx.params_changed(ctx.G)
         return loss
+
+    # ---- CUDA-graph execution of the whole train step (the ~2000 launches of a step are CPU-launch bound) ----
+    def enable_cuda_graph(self, batch_size):
+        """Capture D run + G run (incl. gradient all-reduces and Adam) into one CUDA graph on static input buffers.
+        Subsequent train_step calls copy the two batches into those buffers and replay the graph; the step sizes
+        lr_t of both optimisers are fed through a device scalar."""
+        dev = self.device
+        self._static = [torch.empty((batch_size, 128, 128, 3), device=dev) for _ in range(4)]
+        self._lr_dev = torch.zeros(2, device=dev)
+        self._set_lr_dev()
+        # warm-up (eager) on a side stream: first-call kernel attributes, plan caches, NCCL communicators
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for b in self._static:
+                b.uniform_(-1, 1)
+            snap = (self.ctx.G.data.clone(), self.ctx.D.data.clone(), self.ctx.S.data.clone(), self.t_D, self.t_G,
+                    self.global_step.value, self.ctx.G.m.clone(), self.ctx.G.v.clone(), self.ctx.D.m.clone(),
+                    self.ctx.D.v.clone())
+            self._run_D(self._static[0], self._static[1])
+            self._run_G(self._static[2], self._static[3])
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.ctx.params_changed()           # every weight re-pack must be recorded inside the graph
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            lD = self._run_D(self._static[0], self._static[1])
+            lG = self._run_G(self._static[2], self._static[3])
+        self._graph_losses = (lD, lG)
+        # undo the two warm-up/capture steps' host-side bookkeeping and parameter updates
+        self.ctx.G.data.copy_(snap[0]); self.ctx.D.data.copy_(snap[1]); self.ctx.S.data.copy_(snap[2])
+        self.ctx.G.m.copy_(snap[6]); self.ctx.G.v.copy_(snap[7]); self.ctx.D.m.copy_(snap[8]); self.ctx.D.v.copy_(snap[9])
+        self.t_D, self.t_G, self.global_step.value = snap[3], snap[4], snap[5]
+        self.ctx.params_changed()
+        torch.cuda.synchronize()
+
+    def _set_lr_dev(self):
+        lr = self._current_lr()
+        vals = torch.tensor([ops.adam_lr_t(lr, self.t_D + 1), ops.adam_lr_t(lr, self.t_G + 1)], dtype=torch.float32)
+        self._lr_dev.copy_(vals, non_blocking=True)
 
     def train_step(self, sess=None, feed_dict=None, step=0, batch_size=None, should_write_log=False,
                    should_write_summary=False):
         start_time = time.time()
-        im, fut = self._next_batch(feed_dict)
-        loss_D = self._run_D(im, fut)
-        im, fut = self._next_batch(feed_dict)
-        loss_G = self._run_G(im, fut)
+        if self._graph is not None:
+            im, fut = self._next_batch(feed_dict)
+            self._static[0].copy_(im, non_blocking=True); self._static[1].copy_(fut, non_blocking=True)
+            im, fut = self._next_batch(feed_dict)
+            self._static[2].copy_(im, non_blocking=True); self._static[3].copy_(fut, non_blocking=True)
+            self._set_lr_dev()
+            self._graph.replay()
+            self.t_D += 1; self.t_G += 1; self.global_step.value += 1
+            loss_D, loss_G = self._graph_losses
+        else:
+            im, fut = self._next_batch(feed_dict)
+            loss_D = self._run_D(im, fut)
+            im, fut = self._next_batch(feed_dict)
+            loss_G = self._run_G(im, fut)
         self._last_losses = (loss_D, loss_G)
         if should_write_log:
             ld, lg = float(loss_D.sum().item()), float(loss_G.sum().item())

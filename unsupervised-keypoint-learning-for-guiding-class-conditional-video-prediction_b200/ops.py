@@ -149,9 +149,15 @@ def bce_logits(logits, label, weight, loss, want_grad):
     return d
 
 
-def adam_tf(p, g, m, v, lr, t, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0):
+def adam_lr_t(lr, t, beta1=0.5, beta2=0.999):
+    """TF's bias-corrected step size lr*sqrt(1-beta2^t)/(1-beta1^t)."""
+    import math
+    return lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+
+
+def adam_tf(p, g, m, v, lr, t, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0, lr_t_dev=None):
     _lib.call("kp_adam_tf", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), beta1, beta2, eps, int(t), float(grad_scale),
-              _st())
+              _p(lr_t_dev), _st())
 
 
 def channel_sum(g, out):
