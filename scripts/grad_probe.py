@@ -100,7 +100,11 @@ def run_perf():
     import kp_b200  # noqa: F401
     from kp_b200 import conv, tapconv as tc
     dev = torch.device("cuda:0")
+    only = os.environ.get("PERF_ONLY")
+    reps_env = int(os.environ.get("PERF_REPS", "20"))
     for name, (N, H, W, Cs, k, s, cout) in PERF.items():
+        if only and name not in only.split(","):
+            continue
         xs = [torch.randn((N, H, W, C), device=dev).to(torch.bfloat16) for C in Cs]
         cin = sum(Cs)
         w = torch.randn((k, k, cin, cout), device=dev) / (k * k * cin) ** 0.5
@@ -112,8 +116,8 @@ def run_perf():
         wplan = tc.plan_conv_wgrad(tuple(xs[0].shape), k, s, 0, cout)
         dw = torch.zeros((k, k, cin, cout), device=dev)
 
-        def timeit(fn, reps=20):
-            for _ in range(3):
+        def timeit(fn, reps=reps_env):
+            for _ in range(3 if reps > 1 else 1):
                 fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -47,8 +47,10 @@ def pack_weights(plan, w, row_scale=None, dtype=torch.bfloat16):
     CB = plan.CB
     w3 = w.reshape(k1 * k2, cin, cout)
     if list(plan.pack["taps"]) != list(range(k1 * k2)):     # stride-2 dgrad parity classes use a subset of the taps
-        taps = torch.as_tensor(plan.pack["taps"], device=w.device, dtype=torch.long)
-        w3 = w3.index_select(0, taps)
+        cache = plan.__dict__.setdefault("_taps_dev", {})      # device index tensor, built once (not inside a graph capture)
+        if w.device not in cache:
+            cache[w.device] = torch.as_tensor(plan.pack["taps"], device=w.device, dtype=torch.long)
+        w3 = w3.index_select(0, cache[w.device])
     if plan.pack["mode"] == "fwd":
         if row_scale is not None:
             w3 = w3 * row_scale.view(1, 1, cout)

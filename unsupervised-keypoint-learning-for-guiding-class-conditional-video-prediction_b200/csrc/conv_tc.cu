@@ -3,15 +3,19 @@
 // Serves every convolution of the stage-1 path (reference: layers.conv, models/networks/layers.py:4-10;
 // Vgg19.conv_layer, models/networks/vgg.py:48-55), forward and data-gradient; see include/kp_b200.h.
 //
-// Per CTA: one 128-pixel x BN-channel output tile.
+// PERSISTENT kernel: grid = min(#tiles, SMs x CTAs/SM); every CTA walks output tiles (128 pixels x BN channels)
+// tile = blockIdx.x, blockIdx.x + gridDim.x, ...  Three roles run concurrently and are decoupled by mbarriers:
 //   warp 0     TMA producer  - per K step one 4-D box [TN][TH][TW][CB] of the (shifted) activation view
 //                              (zero fill outside the image = TF zero padding) + one 2-D box [BN][CB] of
-//                              the packed weights, both hardware-swizzled, into an S-stage smem ring;
-//   warp 1     MMA issuer    - tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16, fp32 accumulators
-//                              in TMEM; tcgen05.commit releases ring slots / signals the epilogue;
+//                              the packed weights, both hardware-swizzled, into an S-stage smem ring that
+//                              keeps rolling ACROSS tiles (the next tile's loads start while this tile computes);
+//   warp 1     MMA issuer    - tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16, fp32 accumulators in
+//                              TMEM, DOUBLE BUFFERED (2 x BN columns): tile i+1 accumulates while tile i drains;
 //   warps 2-5  epilogue      - tcgen05.ld 32x32b (one output pixel per thread), optional per-channel
 //                              sum / sum-of-squares (batch-norm statistics) by a warp transpose-reduce +
-//                              atomics, bias + activation, bf16/f32 NHWC stores.
+//                              atomics, bias + activation (+ accumulate), bf16/f32 NHWC stores.
+// (ncu of the first, non-persistent version: tensor pipe 9-21 % active with DRAM/L2/L1 all far from saturated,
+//  i.e. bound by the serial prologue -> main loop -> epilogue chain of each tile; profiles/README.md.)
 #include "kp_tc.cuh"
 #include "kp_internal.h"
 #include <cudaTypedefs.h>
@@ -28,7 +32,7 @@ struct alignas(64) TapConvKParams {
     signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], mf[KP_MAX_TAPS];
     int TW, TH, TN, tiles_w, tiles_h;
     int Ho, Wo, N;
-    int BN, tmem_cols, stages, total_iters;
+    int BN, n_tiles, total_tiles, tmem_cols, stages, total_iters;
     uint32_t a_bytes, b_bytes, stage_bytes;
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
@@ -100,23 +104,22 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
     uint8_t* base = smem_dyn + (smem_base - smem_u32(smem_dyn));
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)p.stages * p.stage_bytes);
     uint64_t* empty = full + p.stages;
-    uint64_t* tfull = empty + p.stages;
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+    uint64_t* tfull = empty + p.stages;   // [2] accumulator buffer ready for the epilogue
+    uint64_t* tempty = tfull + 2;         // [2] accumulator buffer drained
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
-
-    const int mt = blockIdx.x;
-    const int tw_i = mt % p.tiles_w, th_i = (mt / p.tiles_w) % p.tiles_h, tn_i = mt / (p.tiles_w * p.tiles_h);
-    const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
-    const int n_off = blockIdx.y * p.BN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);     // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
@@ -126,132 +129,182 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
     const uint32_t tmem = *tslot;
 
     if (warp == 0) {
+        // ------------------------------- TMA producer -------------------------------
         if (lane == 0) {
             for (int m = 0; m < KP_MAX_MAPS; ++m)
                 if (p.nblk[m] > 0) tma_prefetch_desc(&p.mapA[m]);
             tma_prefetch_desc(&p.mapB);
-            int it = 0;
-            for (int t = 0; t < p.n_taps; ++t) {
-                const int cw = w0 + p.dw[t], ch = h0 + p.dh[t];
-                for (int s = 0; s < p.n_src; ++s) {
-                    const int m = p.mf[t] + s;
-                    const int nb = p.nblk[m];
-                    for (int cb = 0; cb < nb; ++cb, ++it) {
-                        const int st = it % S;
-                        if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
-                        uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
-                        mbar_arrive_expect_tx(&full[st], p.a_bytes + p.b_bytes);
-                        tma_load_4d(a_dst, &p.mapA[m], &full[st], cb * CB, cw, ch, n0);
-                        tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it * CB, n_off);
+            uint32_t git = 0;   // ring position, keeps counting across tiles
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+                const int n_off = nt * p.BN;
+                int it = 0;
+                for (int t = 0; t < p.n_taps; ++t) {
+                    const int cw = w0 + p.dw[t], ch = h0 + p.dh[t];
+                    for (int s = 0; s < p.n_src; ++s) {
+                        const int m = p.mf[t] + s;
+                        const int nb = p.nblk[m];
+                        for (int cb = 0; cb < nb; ++cb, ++it, ++git) {
+                            const uint32_t st = git % (uint32_t)S;
+                            if (git >= (uint32_t)S) mbar_wait(&empty[st], ((git / (uint32_t)S) - 1) & 1);
+                            uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
+                            mbar_arrive_expect_tx(&full[st], p.a_bytes + p.b_bytes);
+                            tma_load_4d(a_dst, &p.mapA[m], &full[st], cb * CB, cw, ch, n0);
+                            tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it * CB, n_off);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
+        // ------------------------------- MMA issuer -------------------------------
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
-            for (int it = 0; it < p.total_iters; ++it) {
-                const int st = it % S;
-                mbar_wait(&full[st], (it / S) & 1);
+            uint32_t git = 0;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                if (lt >= 2) mbar_wait(&tempty[acc], ((lt >> 1) - 1) & 1);   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + (uint32_t)st * p.stage_bytes;
-                const uint32_t b_addr = a_addr + p.a_bytes;
+                const uint32_t d_tmem = tmem + (uint32_t)(acc * p.BN);
+                for (int it = 0; it < p.total_iters; ++it, ++git) {
+                    const uint32_t st = git % (uint32_t)S;
+                    mbar_wait(&full[st], (git / (uint32_t)S) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + st * p.stage_bytes;
+                    const uint32_t b_addr = a_addr + p.a_bytes;
 #pragma unroll
-                for (int k = 0; k < CB / 16; ++k) {
-                    const uint64_t da = umma_smem_desc(a_addr + k * 32, SBO, 16, LAYOUT);
-                    const uint64_t db = umma_smem_desc(b_addr + k * 32, SBO, 16, LAYOUT);
-                    umma_bf16(tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < CB / 16; ++k) {
+                        const uint64_t da = umma_smem_desc(a_addr + k * 32, SBO, 16, LAYOUT);
+                        const uint64_t db = umma_smem_desc(b_addr + k * 32, SBO, 16, LAYOUT);
+                        umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[st]);
                 }
-                umma_commit(&empty[st]);
+                umma_commit(&tfull[acc]);
             }
-            umma_commit(tfull);
         }
     } else {
         // ------------------------------- epilogue -------------------------------
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
-        const int uw = w0 + tw, uh = h0 + th, n = n0 + tn;
-        const bool valid = (uw < p.Wo) && (uh < p.Ho) && (n < p.N);
-        const long long pix = p.out_off + (long long)n * p.out_sn + (long long)uh * p.out_sh + (long long)uw * p.out_sw;
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            float v[16];
-            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-pixel predicated stores
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int ch0 = n_off + c0;
-            if (p.ssum != nullptr) {
-                float sq[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-                const float s1 = warp_colsum16(v, lane);
-                const float s2 = warp_colsum16(sq, lane);
-                if ((lane & 1) == 0) {
-                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    atomicAdd(p.ssum + ch0 + col, s1);
-                    atomicAdd(p.ssq + ch0 + col, s2);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+            const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+            const int n_off = nt * p.BN;
+            const int uw = w0 + tw, uh = h0 + th, n = n0 + tn;
+            const bool valid = (uw < p.Wo) && (uh < p.Ho) && (n < p.N);
+            const long long pix = p.out_off + (long long)n * p.out_sn + (long long)uh * p.out_sh + (long long)uw * p.out_sw;
+            const int acc = lt & 1;
+            mbar_wait(&tfull[acc], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float v[16];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-pixel predicated stores
+                tmem_ld16(t_row + (uint32_t)c0, v);
+                if (c0 + 16 >= p.BN) {
+                    // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-            }
-            if (valid && ch0 < p.Cout) {
-            if (p.bias != nullptr) {
+                const int ch0 = n_off + c0;
+                if (p.ssum != nullptr) {
+                    float sq[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + ch0 + j);
-            }
-            if (p.act != KP_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act, p.alpha, ch0 + j == p.Cout - 1);
-            }
-            const int nvalid = min(16, p.Cout - ch0);
-            if (p.accumulate) {  // out += result (gradient of a tensor with several consumers)
-                if (p.out_f32) {
-                    const float* o = reinterpret_cast<const float*>(p.out) + pix + ch0;
-                    for (int j = 0; j < nvalid; ++j) v[j] += o[j];
-                } else {
-                    const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.out) + pix + ch0;
-                    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-                        float old[16];
-                        const uint4* o4 = reinterpret_cast<const uint4*>(o);
-                        const uint4 u0 = o4[0], u1 = o4[1];
-                        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-                        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+                    for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = warp_colsum16(v, lane);
+                    const float s2 = warp_colsum16(sq, lane);
+                    if ((lane & 1) == 0) {
+                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        atomicAdd(p.ssum + ch0 + col, s1);
+                        atomicAdd(p.ssq + ch0 + col, s2);
+                    }
+                }
+                // Everything below is fully unrolled with compile-time indices so v[] stays in registers, and the
+                // activation is selected by ONE warp-uniform branch per chunk (the first version indexed v[]
+                // dynamically -> local memory, and evaluated the activation switch per element: ~8000 instructions
+                // per warp per tile, which made the whole kernel epilogue-bound).
+                if (valid && ch0 < p.Cout) {
+                    if (p.bias != nullptr) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch0);   // [Cout_pad], 64-byte aligned chunk
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 a = __bfloat1622float2(h0[j]), b = __bfloat1622float2(h1[j]);
-                            old[2 * j] = a.x; old[2 * j + 1] = a.y; old[8 + 2 * j] = b.x; old[8 + 2 * j + 1] = b.y;
+                            const float4 b = __ldg(b4 + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                         }
+                    }
+                    if (p.act == KP_ACT_RELU) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += old[j];
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == KP_ACT_LEAKY) {
+                        const float al = p.alpha;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : al * v[j];
+                    } else if (p.act == KP_ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+                    } else if (p.act == KP_ACT_SIGMOID_LAST) {
+                        const int last = p.Cout - 1 - ch0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j == last) v[j] = 1.f / (1.f + __expf(-v[j]));
+                    }
+                    const int nvalid = p.Cout - ch0;   // >= 1; the chunk is complete when >= 16
+                    if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
+                        if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                            float4* o4 = reinterpret_cast<float4*>(o);
+                            if (p.accumulate) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 b = o4[j];
+                                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < nvalid) o[j] = p.accumulate ? o[j] + v[j] : v[j];
+                        }
                     } else {
-                        for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(o[j]);
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + ch0;
+                        if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                            uint4* o4 = reinterpret_cast<uint4*>(o);
+                            if (p.accumulate) {
+                                const uint4 u0 = o4[0], u1 = o4[1];
+                                const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&u0);
+                                const __nv_bfloat162* h1p = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 a = __bfloat1622float2(h0p[j]), b = __bfloat1622float2(h1p[j]);
+                                    v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+                                }
+                            }
+                            uint32_t w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < nvalid)
+                                    o[j] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[j]) + v[j] : v[j]);
+                        }
                     }
                 }
-            }
-            if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
-                if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-                    float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                    for (int j = 0; j < nvalid; ++j) o[j] = v[j];
-                }
-            } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + ch0;
-                if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-                    uint32_t w[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        w[j] = *reinterpret_cast<uint32_t*>(&h2);
-                    }
-                    uint4* o4 = reinterpret_cast<uint4*>(o);
-                    o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                } else {
-                    for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(v[j]);
-                }
-            }
             }
         }
     }
@@ -284,6 +337,17 @@ static EncodeTiledFn get_encode_fn() {
 
 static CUtensorMapSwizzle swizzle_for(int CB) {
     return CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;
+    }
+    return sms;
 }
 
 // Encode a strided [N][Hd][Wd][C] bf16 view as a 4-D tiled tensor map with box {CB, TW, TH, TN}.
@@ -405,30 +469,31 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     const int tiles_n = (d->N + TN - 1) / TN;
     p.Ho = d->Ho; p.Wo = d->Wo; p.N = d->N;
     p.BN = BN;
-    p.tmem_cols = pow2_at_least(BN, 32);
+    p.n_tiles = d->Cout_pad / BN;
+    p.total_tiles = p.tiles_w * p.tiles_h * tiles_n * p.n_tiles;
+    p.tmem_cols = pow2_at_least(2 * BN, 32);          // double-buffered accumulator
     p.total_iters = total_iters;
     p.a_bytes = 128u * CB * 2u;
     p.b_bytes = (uint32_t)BN * CB * 2u;
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
-    // Shared-memory budget per CTA.  The kernel is not persistent, so prologue / main loop / epilogue of different
-    // tiles only overlap when several CTAs share an SM: small tiles get a shallow ring (3 CTAs/SM), medium ones 2
-    // CTAs/SM, and only the 256-wide tiles take the whole SM (KP_TAPCONV_SMEM_KB overrides, for experiments).
-    uint32_t budget = p.stage_bytes <= 24u * 1024u ? 72u * 1024u : p.stage_bytes <= 32u * 1024u ? 100u * 1024u : 200u * 1024u;
+    // CTAs per SM: two independent pipelines per SM hide the barrier round trips of the single-thread TMA / MMA
+    // issuers; the 256-wide tiles need all 512 TMEM columns and most of the shared memory, so they run alone.
+    int ctas_per_sm = p.tmem_cols <= 256 ? 2 : 1;
+    if (const char* e = getenv("KP_TAPCONV_CTAS_PER_SM")) ctas_per_sm = atoi(e) >= 2 && p.tmem_cols <= 256 ? 2 : 1;
+    uint32_t budget = ctas_per_sm == 2 ? 100u * 1024u : 200u * 1024u;
     if (const char* e = getenv("KP_TAPCONV_SMEM_KB")) budget = (uint32_t)atoi(e) * 1024u;
     int stages = (int)(budget / p.stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > 8) stages = 8;
-    if (stages > total_iters) stages = total_iters;
-    if (stages < 1) stages = 1;
     p.stages = stages;
     p.out = out;
     p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
     p.Cout = d->Cout; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate;
     p.bias = bias; p.ssum = ssum; p.ssq = ssq;
 
-    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)(d->Cout_pad / BN), 1);
-    KP_REQUIRE(grid.y <= 65535, "kp_tapconv: too many channel tiles");
+    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    int grid = device_sm_count() * ctas_per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
 #define KP_LAUNCH_TAPCONV(CBV)                                                                                      \
     do {                                                                                                            \
         static bool attr_done = false;                                                                              \

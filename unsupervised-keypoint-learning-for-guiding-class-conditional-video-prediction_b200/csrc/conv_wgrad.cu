@@ -3,13 +3,19 @@
 //   dW[tap][ci][co] += sum_pixels X_tap[pixel][ci] * dY[pixel][co]
 //
 // M = ci (128 rows per CTA), N = co (BN <= 256), K = pixels.  Both operands arrive exactly as in the forward
-// kernel - TMA 4-D boxes [64 pixels][CB channels], hardware swizzled - and are consumed as MN-major UMMA
+// kernel - TMA 4-D boxes [KP pixels][CB channels], hardware swizzled - and are consumed as MN-major UMMA
 // operands (channels contiguous), so no transposed copy of X or dY exists anywhere.
-// grid = (ci blocks x co blocks, taps, pixel splits); fp32 partial tiles are accumulated into the HWIO
-// gradient with atomic adds.
+//
+// TAP SHARING: one CTA accumulates T taps of the same pixel range at once (T accumulators of BN columns in TMEM):
+// the dY tile is loaded once per pipeline stage and reused by the T shifted X tiles, which divides the dY traffic
+// and the number of pipeline round trips per FLOP by T (the first version launched one CTA per tap and was bound
+// by L2 re-reads of dY for the small-channel 128x128 layers and by its atomic epilogue everywhere).
+// grid = (ci blocks x co blocks, tap groups, pixel splits); fp32 partial tiles are accumulated into the HWIO
+// gradient with vectorised red.global.add.v4.f32.
 #include "kp_tc.cuh"
 #include "kp_internal.h"
 #include <string.h>
+#include <stdlib.h>
 
 namespace kp {
 
@@ -22,11 +28,17 @@ struct alignas(64) WgradKParams {
     signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], mf[KP_MAX_TAPS];
     int tap_flat[KP_MAX_TAPS];
     int TW, TH, TN, tiles_w, tiles_h, total_tiles, tiles_per_split;
+    int n_taps, T;                       // taps per CTA (group size)
     int Cin, Cout, BN, co_blocks, tmem_cols, stages;
-    uint32_t box_bytes, a_bytes, stage_bytes;
+    int n_a_max, n_b_max;
+    uint32_t box_bytes, stage_bytes;
     float* dw_out;
     long long dw_off, dw_stap, dw_sci;
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int CB>
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
@@ -48,13 +60,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     const int S = p.stages;
     const int ci0 = (blockIdx.x / p.co_blocks) * 128;
     const int co0 = (blockIdx.x % p.co_blocks) * p.BN;
-    const int tap = blockIdx.y;
+    const int tap0 = blockIdx.y * p.T;
+    const int nt = min(p.T, p.n_taps - tap0);
     const int t_begin = blockIdx.z * p.tiles_per_split;
     const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
     const int n_iters = t_end - t_begin;  // host guarantees >= 1
 
     const int n_a = min(128 / CB, (p.Cin - ci0 + CB - 1) / CB);
     const int n_b = (min(p.BN, p.Cout - co0) + CB - 1) / CB;
+    // stage layout: [dY: n_b_max boxes][X of tap 0: n_a_max boxes][X of tap 1] ...
+    const uint32_t x_region = (uint32_t)p.n_a_max * p.box_bytes;
+    const uint32_t dy_region = (uint32_t)p.n_b_max * p.box_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -72,11 +88,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 
     if (warp == 0) {
         if (lane == 0) {
-            const CUtensorMap* mx = &p.mapX[p.mf[tap]];
-            tma_prefetch_desc(mx);
             tma_prefetch_desc(&p.mapDY);
-            const int dh = p.dh[tap], dw = p.dw[tap];
-            const uint32_t tx = (uint32_t)(n_a + n_b) * p.box_bytes;
+            for (int m = 0; m < KP_MAX_MAPS; ++m)
+                if (m == 0 || p.mf[tap0] == m) tma_prefetch_desc(&p.mapX[m]);
+            const uint32_t tx = (uint32_t)(nt * n_a + n_b) * p.box_bytes;
             for (int it = 0; it < n_iters; ++it) {
                 const int tile = t_begin + it;
                 const int w0 = (tile % p.tiles_w) * p.TW;
@@ -84,13 +99,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                 const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
                 const int st = it % S;
                 if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
-                uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
-                uint8_t* b_dst = a_dst + p.a_bytes;
+                uint8_t* dy_dst = base + (size_t)st * p.stage_bytes;
                 mbar_arrive_expect_tx(&full[st], tx);
-                for (int c = 0; c < n_a; ++c)
-                    tma_load_4d(a_dst + (size_t)c * p.box_bytes, mx, &full[st], ci0 + c * CB, w0 + dw, h0 + dh, n0);
                 for (int c = 0; c < n_b; ++c)
-                    tma_load_4d(b_dst + (size_t)c * p.box_bytes, &p.mapDY, &full[st], co0 + c * CB, w0, h0, n0);
+                    tma_load_4d(dy_dst + (size_t)c * p.box_bytes, &p.mapDY, &full[st], co0 + c * CB, w0, h0, n0);
+                for (int ti = 0; ti < nt; ++ti) {
+                    const int t = tap0 + ti;
+                    uint8_t* x_dst = dy_dst + dy_region + (size_t)ti * x_region;
+                    for (int c = 0; c < n_a; ++c)
+                        tma_load_4d(x_dst + (size_t)c * p.box_bytes, &p.mapX[p.mf[t]], &full[st], ci0 + c * CB, w0 + p.dw[t],
+                                    h0 + p.dh[t], n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -100,13 +119,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                 const int st = it % S;
                 mbar_wait(&full[st], (it / S) & 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + (uint32_t)st * p.stage_bytes;
-                const uint32_t b_addr = a_addr + p.a_bytes;
+                const uint32_t dy_addr = smem_base + (uint32_t)st * p.stage_bytes;
+                for (int ti = 0; ti < nt; ++ti) {
+                    const uint32_t x_addr = dy_addr + dy_region + (uint32_t)ti * x_region;
+                    const uint32_t d_tmem = tmem + (uint32_t)(ti * p.BN);
 #pragma unroll
-                for (int kk = 0; kk < KP / 16; ++kk) {
-                    const uint64_t da = umma_smem_desc(a_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
-                    const uint64_t db = umma_smem_desc(b_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
-                    umma_bf16(tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < KP / 16; ++kk) {
+                        const uint64_t da = umma_smem_desc(x_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
+                        const uint64_t db = umma_smem_desc(dy_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
+                        umma_bf16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty[st]);
             }
@@ -116,18 +138,26 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         const int q = warp & 3;
         const int ci = ci0 + q * 32 + lane;
         const bool valid = ci < p.Cin;
-        float* orow = p.dw_out + p.dw_off + (long long)p.tap_flat[tap] * p.dw_stap + (long long)ci * p.dw_sci;
         mbar_wait(tfull, 0);
         tc_fence_after();
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            float v[16];
-            __syncwarp();
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (valid) {
+        for (int ti = 0; ti < nt; ++ti) {
+            float* orow = p.dw_out + p.dw_off + (long long)p.tap_flat[tap0 + ti] * p.dw_stap + (long long)ci * p.dw_sci + co0;
+            const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ti * p.BN);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float v[16];
+                __syncwarp();
+                tmem_ld16(t_row + (uint32_t)c0, v);
+                if (valid) {
+                    const int nvalid = p.Cout - co0 - c0;
+                    float* o = orow + c0;
+                    if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int co = co0 + c0 + j;
-                    if (co < p.Cout) atomicAdd(orow + co, v[j]);
+                        for (int j = 0; j < 4; ++j) red_add_v4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nvalid) atomicAdd(o + j, v[j]);
+                    }
                 }
             }
         }
@@ -136,6 +166,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
+
+int device_sm_count();
 
 int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
     KP_REQUIRE(d->CB == 16 || d->CB == 32 || d->CB == 64, "kp_wgrad: CB must be 16, 32 or 64 (got %d)", d->CB);
@@ -158,6 +190,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
         KP_REQUIRE(d->map_first[t] >= 0 && d->map_first[t] < d->n_maps, "kp_wgrad: tap %d map out of range", t);
         p.dh[t] = d->dh[t]; p.dw[t] = d->dw[t]; p.mf[t] = d->map_first[t]; p.tap_flat[t] = d->tap_flat[t];
     }
+    p.n_taps = d->n_taps;
     p.tiles_w = (d->Wo + p.TW - 1) / p.TW;
     p.tiles_h = (d->Ho + p.TH - 1) / p.TH;
     p.total_tiles = p.tiles_w * p.tiles_h * ((d->N + p.TN - 1) / p.TN);
@@ -166,41 +199,51 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     p.BN = cout_pad <= 256 ? cout_pad : 256;
     p.co_blocks = (cout_pad + p.BN - 1) / p.BN;
     const int ci_blocks = (d->Cin + 127) / 128;
-    int tm = 32;
-    while (tm < p.BN) tm <<= 1;
-    p.tmem_cols = tm;
     p.box_bytes = (uint32_t)wg_kp(CB) * CB * 2u;                          // 8 KB
-    // A region holds only the channel chunks that exist (the MMA still reads 128 rows = 128/CB chunks at LBO
-    // stride: the rows past the loaded chunks alias the B region / next stage / the slack below and produce
+    // X regions hold only the channel chunks that exist (the MMA still reads 128 rows = 128/CB chunks at LBO stride:
+    // rows past the loaded chunks alias the next tap's region / the next stage / the slack below and only produce
     // accumulator rows that are never stored)
-    const int n_a_max = ((d->Cin < 128 ? d->Cin : 128) + CB - 1) / CB;
-    p.a_bytes = (uint32_t)n_a_max * p.box_bytes;
-    const uint32_t b_bytes = (uint32_t)((p.BN + CB - 1) / CB) * p.box_bytes;
-    p.stage_bytes = (p.a_bytes + b_bytes + 1023u) & ~1023u;
+    p.n_a_max = ((d->Cin < 128 ? d->Cin : 128) + CB - 1) / CB;
+    p.n_b_max = (p.BN + CB - 1) / CB;
+    // taps per CTA: limited by TMEM (T accumulators of BN columns) and by shared memory (<= 11 boxes = 88 KB per stage)
+    int t_max = 512 / p.BN;
+    const size_t slack = (size_t)(128 / CB - p.n_a_max) * p.box_bytes;
+    const int boxes_per_stage = (int)(((215u * 1024u - slack) / 2) / p.box_bytes);   // two stages must fit
+    const int by_smem = (boxes_per_stage - p.n_b_max) / p.n_a_max;
+    if (t_max > by_smem) t_max = by_smem;
+    if (t_max > d->n_taps) t_max = d->n_taps;
+    if (const char* e = getenv("KP_WGRAD_TMAX")) { const int c = atoi(e); if (c >= 1 && c < t_max) t_max = c; }
+    if (t_max < 1) t_max = 1;
+    const int groups = (d->n_taps + t_max - 1) / t_max;
+    p.T = (d->n_taps + groups - 1) / groups;
+    int tm = 32;
+    while (tm < p.T * p.BN) tm <<= 1;
+    p.tmem_cols = tm;
+    p.stage_bytes = (uint32_t)(p.T * p.n_a_max + p.n_b_max) * p.box_bytes;
+    int stages = (int)((215u * 1024u - slack) / p.stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 2) stages = 2;
+    const int ctas_per_sm = ((size_t)stages * p.stage_bytes <= 100u * 1024u && tm <= 256) ? 2 : 1;
     int splits = d->splits;
-    const int base_ctas = ci_blocks * p.co_blocks * d->n_taps;
+    const int base_ctas = ci_blocks * p.co_blocks * groups;
     if (splits <= 0) {
-        splits = (3 * 148 + base_ctas - 1) / base_ctas;
-        const int max_by_work = (p.total_tiles + 7) / 8;   // at least ~8 pixel tiles per CTA
+        const int target = device_sm_count() * ctas_per_sm;
+        splits = (target + base_ctas - 1) / base_ctas;
+        const int max_by_work = (p.total_tiles + 7) / 8;   // at least ~8 pixel tiles per CTA (amortises the red epilogue)
         if (splits > max_by_work) splits = max_by_work;
     }
     if (splits < 1) splits = 1;
     if (splits > p.total_tiles) splits = p.total_tiles;
     p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
     splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-    int stages = (int)((96u * 1024u) / p.stage_bytes);       // ~2 CTAs per SM
-    if (stages < 2) stages = 2;
-    if (stages > 6) stages = 6;
-    if (stages > p.tiles_per_split) stages = p.tiles_per_split;
-    if (stages < 1) stages = 1;
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split < 1 ? 1 : p.tiles_per_split;
     p.stages = stages;
     p.dw_out = dw;
     p.dw_off = d->dw_off; p.dw_stap = d->dw_stap; p.dw_sci = d->dw_sci;
 
-    const uint32_t over_read = (uint32_t)(128 / CB) * p.box_bytes;
-    const size_t slack = over_read > p.stage_bytes ? over_read - p.stage_bytes : 0;
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024 + slack;
-    dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)d->n_taps, (unsigned)splits);
+    KP_REQUIRE(smem <= 227u * 1024u, "kp_wgrad: shared memory %zu exceeds the SM (internal tiling error)", smem);
+    dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)groups, (unsigned)splits);
 #define KP_LAUNCH_WGRAD(CBV)                                                                                     \
     do {                                                                                                         \
         static bool attr_done = false;                                                                           \
