@@ -161,6 +161,20 @@ typedef struct {
 
 int kp_tapconv_wgrad_bf16(const kp_wgrad_desc* desc, const void* x, const void* dy, float* dw, void* stream);
 
+/* Weight re-layout for the tap-GEMMs: fp32 HWIO kernel [k*k][cin][cout] -> bf16 K-major [rows_pad][Ktot]
+ * (Ktot = T*Kper).  mode 0 (forward): row = co, K = taps x channel-concat segments each padded to the channel
+ * block, optional per-output-channel scale (batch-norm folding).  mode 1 (data gradient): row = ci - c0,
+ * K = taps x cout padded to the channel block.  Pure data movement + cast, one launch.                 */
+typedef struct {
+    int mode;                              /* 0 forward, 1 data gradient */
+    int T; int tap_flat[KP_MAX_TAPS];      /* taps used, as rows kh*k+kw of the HWIO kernel */
+    int cin, cout;                         /* source kernel dims */
+    int nseg; int seg_start[3], seg_count[3], seg_kbase[3];   /* mode 0: source channel range -> K offset */
+    int c0, rows;                          /* mode 1: first input channel and number of rows */
+    int Kper, rows_pad, Ktot;
+} kp_pack_desc;
+int kp_pack_weights(const float* w, const kp_pack_desc* desc, const float* row_scale, void* dst, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Memory-bound companions (bf16 NHWC, 8-channel vectors; fp32 only at the reference boundary)
  * ------------------------------------------------------------------------------------------- */

@@ -300,3 +300,29 @@ def test_detector_inference_matches_oracle(cuda_dev):
     octx = ON.Ctx(P)
     ref = ON.pose_encoder(octx, im[0], 40, False)
     assert (out["pts"][0].cpu() - ref).abs().max().item() <= 1e-4
+
+
+def test_pack_weights_kernel_matches_recipe(cuda_dev):
+    """kp_pack_weights (one launch) == the numpy recipe the CPU lowering tests pin against the conv oracle (bit-exact
+    after the bf16 cast), for forward (concat segments, channel tails, BN-fold scale) and data-gradient layouts."""
+    from kp_b200 import conv, tapconv as tc
+    rng = np.random.default_rng(21)
+    cases = [([(2, 8, 8, 16), (2, 8, 8, 32)], 3, 1, 0, 24), ([(1, 8, 8, 40)], 3, 1, 0, 16), ([(1, 16, 16, 64)], 4, 2, 1, 128),
+             ([(1, 8, 8, 16)], 7, 1, 0, 32), ([(1, 8, 8, 128), (1, 8, 8, 40), (1, 8, 8, 40)], 3, 1, 0, 256)]
+    for shapes, k, s, pad, cout in cases:
+        cin = sum(sh[3] for sh in shapes)
+        w = rng.normal(size=(k, k, cin, cout)).astype(np.float32)
+        wd = torch.from_numpy(w).to(cuda_dev)
+        plan, _ = tc.plan_conv_fwd(shapes, k, s, pad, cout)
+        ref = torch.from_numpy(tc.pack_weights_np(plan, w)).to(torch.bfloat16)
+        assert torch.equal(conv.pack_weights(plan, wd).cpu(), ref)
+        assert torch.equal(conv.pack_weights_torch(plan, wd).cpu(), ref)
+        scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        ref_s = torch.from_numpy(tc.pack_weights_np(plan, w * scale.reshape(1, 1, 1, cout))).to(torch.bfloat16)
+        assert torch.equal(conv.pack_weights(plan, wd, row_scale=torch.from_numpy(scale).to(cuda_dev)).cpu(), ref_s)
+        c0 = 0
+        for sh in shapes:
+            for p in tc.plan_conv_dgrad(sh, k, s, pad, cout if cout % 8 == 0 else cout, cin_slice=(c0, c0 + sh[3], cin)):
+                ref_d = torch.from_numpy(tc.pack_weights_np(p, w)).to(torch.bfloat16)
+                assert torch.equal(conv.pack_weights(p, wd).cpu(), ref_d)
+            c0 += sh[3]

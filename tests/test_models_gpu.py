@@ -99,22 +99,26 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
             return batches[cur["i"] % 4]
         m.build(feed)
         return m
-    eager, graph = make(), make()
+    eager, eager2, graph = make(), make(), make()
     graph.enable_cuda_graph(B)
     assert torch.equal(eager.ctx.G.data, graph.ctx.G.data) and int(graph.global_step.value) == 0
     for _ in range(2):
         eager.train_step()
+        eager2.train_step()
         graph.train_step()
     torch.cuda.synchronize()
     assert int(graph.global_step.value) == 2 and graph.t_G == 2
     le = torch.cat(eager._last_losses).cpu()
     lg = torch.cat(graph._last_losses).cpu()
     assert torch.allclose(le, lg, rtol=2e-2, atol=1e-3), (le, lg)
-    # Adam's first steps are sign-like (|step| ~ lr): compare the parameter change statistically
-    for grp_e, grp_g in ((eager.ctx.G, graph.ctx.G), (eager.ctx.D, graph.ctx.D)):
-        diff = (grp_e.data - grp_g.data).abs()
-        assert diff.max().item() <= 6e-4              # a few lr-sized (1e-4) sign-like steps apart at worst
-        assert diff.mean().item() <= 2e-5             # and the overwhelming majority identical to rounding
+    # The step is not bit-reproducible run to run (fp32 atomics in the BN statistics / weight gradients, then bf16
+    # rounding and ReLU masks amplify the last-bit differences), and Adam's first steps are sign-like (|step| ~ lr):
+    # so a graph replay must differ from an eager run by no more than two eager runs differ from each other.
+    for grp_e, grp_e2, grp_g in ((eager.ctx.G, eager2.ctx.G, graph.ctx.G), (eager.ctx.D, eager2.ctx.D, graph.ctx.D)):
+        d_graph = (grp_e.data - grp_g.data).abs()
+        d_eager = (grp_e.data - grp_e2.data).abs()
+        assert d_graph.max().item() <= 6e-4           # a few lr-sized (1e-4) steps apart at worst
+        assert d_graph.mean().item() <= 2.0 * d_eager.mean().item() + 2e-5, (d_graph.mean().item(), d_eager.mean().item())
 
 
 def test_final_model_outputs(cuda_dev):

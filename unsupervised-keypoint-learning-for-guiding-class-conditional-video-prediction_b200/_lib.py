@@ -51,6 +51,7 @@ SIGNATURES = {
     "kp_bce_logits_fwd_bwd": [c_vp, c_int, c_float, c_float, c_vp, c_vp, c_vp],
     "kp_adam_tf": [c_vp, c_vp, c_vp, c_vp, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, c_vp, c_vp],
     "kp_channel_sum": [c_vp, c_ll, c_int, c_vp, c_vp],
+    "kp_pack_weights": [c_vp, c_vp, c_vp, c_vp, c_vp],
 }
 _RESTYPES = {"kp_last_error": ctypes.c_char_p, "kp_launch_count": ctypes.c_ulonglong}
 

@@ -37,12 +37,28 @@ class _Timed:
             PROFILE.append((self.kind, self.flops, self.e0, self.e1))
 
 
-def pack_weights(plan, w, row_scale=None, dtype=torch.bfloat16):
-    """HWIO float kernel [k,k,Cin,Cout] -> packed [rows_pad, Ktot] bf16 (K-major) following plan.pack.
+def pack_weights(plan, w, row_scale=None):
+    """HWIO float kernel [k,k,Cin,Cout] -> packed [rows_pad, Ktot] bf16 (K-major) following plan.pack, in ONE
+    kernel launch (kp_pack_weights).  `row_scale` (fwd mode, [Cout]) multiplies each output channel's weights
+    (batch-norm folding).  Same recipe as tapconv.pack_weights_np, which the CPU tests pin against the conv oracle."""
+    if not (w.is_cuda and w.dtype == torch.float32):
+        raise ValueError("pack_weights: w must be a float32 CUDA tensor")
+    w = w.contiguous()
+    d = tc.pack_desc(plan, tuple(w.shape))
+    out = torch.empty((plan.rows_pad, plan.Ktot), device=w.device, dtype=torch.bfloat16)
+    rs = None
+    if row_scale is not None:
+        if plan.pack["mode"] != "fwd":
+            raise ValueError("row_scale only applies to forward packing")
+        rs = row_scale.to(torch.float32).contiguous()
+    with torch.cuda.device(w.device):
+        _lib.call("kp_pack_weights", w.data_ptr(), ctypes.byref(d), None if rs is None else rs.data_ptr(), out.data_ptr(),
+                  _stream())
+    return out
 
-    `row_scale` (fwd mode, [Cout]) multiplies each output channel's weights (batch-norm folding).
-    Mirrors tapconv.pack_weights_np (which the CPU tests pin against the conv oracle).
-    """
+
+def pack_weights_torch(plan, w, row_scale=None, dtype=torch.bfloat16):
+    """Reference re-layout with torch ops (tests cross-check the kernel above against it)."""
     k1, k2, cin, cout = w.shape
     CB = plan.CB
     w3 = w.reshape(k1 * k2, cin, cout)

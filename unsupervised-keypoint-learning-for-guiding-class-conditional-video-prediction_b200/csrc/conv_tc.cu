@@ -417,6 +417,11 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     KP_REQUIRE(TW * TH * TN == 128, "kp_tapconv: tile %dx%dx%d is not 128 pixels", TW, TH, TN);
     if (BN <= 0) {
         BN = d->Cout_pad <= 256 ? d->Cout_pad : (d->Cout_pad % 256 == 0 ? 256 : 128);
+        // Under-filled launches (few pixel tiles: 16x16 layers, img_discr conv_3..5): halve the channel tile until the
+        // tile count reaches ~the SM count; per-tile efficiency drops a little, idle SMs cost a lot.
+        const long long m_tiles = (long long)((d->Wo + TW - 1) / TW) * ((d->Ho + TH - 1) / TH) * ((d->N + TN - 1) / TN);
+        while (BN >= 128 && BN % 32 == 0 && m_tiles * (d->Cout_pad / BN) < (long long)(device_sm_count() * 3) / 4)
+            BN /= 2;
         if (const char* e = getenv("KP_TAPCONV_BN_MAX")) {   // experiments: cap the channel tile
             const int cap = atoi(e);
             if (cap >= 16 && cap % 16 == 0 && BN > cap && d->Cout_pad % cap == 0) BN = cap;

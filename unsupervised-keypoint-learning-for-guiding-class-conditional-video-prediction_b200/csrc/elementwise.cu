@@ -107,59 +107,82 @@ __global__ void bn_finalize_kernel(const float* __restrict__ ssum, const float* 
 
 // y = relu(x*scale + shift) (scale == nullptr: identity), optionally followed by the legacy bilinear x2
 // upsampling (out[2i] = in[i], out[2i+1] = (in[i] + in[min(i+1,n-1)])/2 on each axis).
+// Per-channel scale/shift live in shared memory (two LDS.128 per 8-channel vector instead of 16 global loads).
+// Plain variant: pure streaming, two independent vectors per loop trip.  UPSAMPLE variant: one thread per INPUT
+// pixel-vector produces the 2x2 output block (4 normalised loads feed 4 stores, instead of up to 4 loads per store).
 template <bool UPSAMPLE>
-__global__ void bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, int relu, int N, int H, int W, int C,
-                                    __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                    int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float sp[];   // [2][C]
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        sp[i] = scale ? scale[i] : 1.f;
+        sp[C + i] = scale ? shift[i] : 0.f;
+    }
+    __syncthreads();
     const int CG = C >> 3;
-    const int Ho = UPSAMPLE ? 2 * H : H, Wo = UPSAMPLE ? 2 * W : W;
-    const long long total = (long long)N * Ho * Wo * CG;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(idx % CG);
-        long long pix = idx / CG;
-        const int wo = (int)(pix % Wo);
-        pix /= Wo;
-        const int ho = (int)(pix % Ho);
-        const int n = (int)(pix / Ho);
-        float sc[8], sh[8];
+    const long long total = (long long)N * H * W * CG;   // input vectors
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto norm = [&](const uint4& u, int cg, float* f) {
+        bf8_unpack(u, f);
+        const float4 s0 = *reinterpret_cast<const float4*>(sp + cg * 8), s1 = *reinterpret_cast<const float4*>(sp + cg * 8 + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(sp + C + cg * 8), h1 = *reinterpret_cast<const float4*>(sp + C + cg * 8 + 4);
+        f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+        f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+        if (relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sc[j] = scale ? scale[cg * 8 + j] : 1.f;
-            sh[j] = scale ? shift[cg * 8 + j] : 0.f;
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        auto load = [&](int h, int w, float* f) {
-            bf8_unpack(*reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + cg * 8), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                f[j] = fmaf(f[j], sc[j], sh[j]);
-                if (relu) f[j] = fmaxf(f[j], 0.f);
-            }
-        };
-        float r[8];
-        if (!UPSAMPLE) {
-            load(ho, wo, r);
-        } else {
-            const int h0 = ho >> 1, w0 = wo >> 1;
-            const int h1 = min(h0 + (ho & 1), H - 1), w1 = min(w0 + (wo & 1), W - 1);
+    };
+    const uint4* x4 = reinterpret_cast<const uint4*>(x);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    if (!UPSAMPLE) {
+        long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; idx + stride < total; idx += 2 * stride) {
+            const uint4 u0 = x4[idx], u1 = x4[idx + stride];
+            float f0[8], f1[8];
+            norm(u0, (int)(idx % CG), f0);
+            norm(u1, (int)((idx + stride) % CG), f1);
+            o4[idx] = bf8_pack(f0);
+            o4[idx + stride] = bf8_pack(f1);
+        }
+        if (idx < total) {
+            float f0[8];
+            norm(x4[idx], (int)(idx % CG), f0);
+            o4[idx] = bf8_pack(f0);
+        }
+    } else {
+        const int Wo = 2 * W;
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+            const int cg = (int)(idx % CG);
+            long long pix = idx / CG;
+            const int w = (int)(pix % W);
+            pix /= W;
+            const int h = (int)(pix % H);
+            const int n = (int)(pix / H);
+            const int w1 = min(w + 1, W - 1), h1 = min(h + 1, H - 1);
+            const long long rowb = ((long long)n * H + h) * W, rowc = ((long long)n * H + h1) * W;
             float a[8], b[8], c[8], d[8];
-            load(h0, w0, a);
-            if (wo & 1) load(h0, w1, b);
-            if (ho & 1) load(h1, w0, c);
-            if ((ho & 1) && (wo & 1)) load(h1, w1, d);
+            norm(x4[(rowb + w) * CG + cg], cg, a);
+            norm(x4[(rowb + w1) * CG + cg], cg, b);
+            norm(x4[(rowc + w) * CG + cg], cg, c);
+            norm(x4[(rowc + w1) * CG + cg], cg, d);
+            float o01[8], o10[8], o11[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                // TF computes top/bottom row lerps along x first, then the lerp along y
-                const float top = (wo & 1) ? a[j] + (b[j] - a[j]) * 0.5f : a[j];
-                if (ho & 1) {
-                    const float bot = (wo & 1) ? c[j] + (d[j] - c[j]) * 0.5f : c[j];
-                    r[j] = top + (bot - top) * 0.5f;
-                } else {
-                    r[j] = top;
-                }
+                // TF computes the top/bottom row lerps along x first, then the lerp along y
+                const float top = a[j] + (b[j] - a[j]) * 0.5f;
+                const float bot = c[j] + (d[j] - c[j]) * 0.5f;
+                o01[j] = top;
+                o10[j] = a[j] + (c[j] - a[j]) * 0.5f;
+                o11[j] = top + (bot - top) * 0.5f;
             }
+            const long long ob = (((long long)n * 2 * H + 2 * h) * Wo + 2 * w) * CG + cg;
+            o4[ob] = bf8_pack(a);
+            o4[ob + CG] = bf8_pack(o01);
+            o4[ob + (long long)Wo * CG] = bf8_pack(o10);
+            o4[ob + (long long)Wo * CG + CG] = bf8_pack(o11);
         }
-        *reinterpret_cast<uint4*>(out + idx * 8) = bf8_pack(r);
     }
 }
 
@@ -214,13 +237,7 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
         mu[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j];
         sb[j] = 0.f; sg[j] = 0.f;
     }
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
-        const int w = (int)(p % W);
-        const int h = (int)((p / W) % H);
-        const int n = (int)(p / ((long long)W * H));
-        float g[8], xv[8];
-        gather_dact<UPSAMPLE>(dout, n, h, w, cg, H, W, C, g);
-        bf8_unpack(*reinterpret_cast<const uint4*>(x + p * C + cg * 8), xv);
+    auto accum = [&](const float* g, const float* xv) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float z = fmaf(xv[j], sc[j], sh[j]);
@@ -228,6 +245,29 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
             sb[j] += gj;
             sg[j] = fmaf(gj, (xv[j] - mu[j]) * rs[j], sg[j]);
         }
+    };
+    const long long pstride = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + pl;
+    if (!UPSAMPLE) {
+        // two independent pixel-vectors per trip (4 x 16-byte loads in flight per thread)
+        for (; p + pstride < P; p += 2 * pstride) {
+            const uint4 g0 = *reinterpret_cast<const uint4*>(dout + p * C + cg * 8);
+            const uint4 x0 = *reinterpret_cast<const uint4*>(x + p * C + cg * 8);
+            const uint4 g1 = *reinterpret_cast<const uint4*>(dout + (p + pstride) * C + cg * 8);
+            const uint4 x1 = *reinterpret_cast<const uint4*>(x + (p + pstride) * C + cg * 8);
+            float g[8], xv[8];
+            bf8_unpack(g0, g); bf8_unpack(x0, xv); accum(g, xv);
+            bf8_unpack(g1, g); bf8_unpack(x1, xv); accum(g, xv);
+        }
+    }
+    for (; p < P; p += pstride) {
+        const int w = (int)(p % W);
+        const int h = (int)((p / W) % H);
+        const int n = (int)(p / ((long long)W * H));
+        float g[8], xv[8];
+        gather_dact<UPSAMPLE>(dout, n, h, w, cg, H, W, C, g);
+        bf8_unpack(*reinterpret_cast<const uint4*>(x + p * C + cg * 8), xv);
+        accum(g, xv);
     }
     __shared__ float red[2][256 * 8 / 1];  // [2][threads][8] would be 16 KB; reuse by striding below
     // reduce over pixel lanes sharing a channel group
@@ -254,35 +294,47 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
 }
 
 // pass 2: dx = gamma*rstd*(g - dbeta/n - xhat*dgamma/n)   (bf16), gamma*rstd == scale
+// With xhat = (x-mean)*rstd the formula is affine in (g, x): dx = sc*g + k1*x + k0, k1 = -sc*rstd*dgamma/n,
+// k0 = -sc*dbeta/n - k1*mean.  The four per-channel coefficients (sc, sh for the mask, k1, k0) sit in shared memory.
 template <bool UPSAMPLE>
-__global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
-                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                        const float* __restrict__ dbeta, const float* __restrict__ dgamma, int relu, int N,
-                                        int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                        const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                        int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+    extern __shared__ float sp[];   // [4][C]: sc, sh, k1, k0
+    const float inv_n = 1.0f / (float)((long long)N * H * W);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float sc = scale[c];
+        const float k1 = -sc * rstd[c] * dgamma[c] * inv_n;
+        sp[c] = sc;
+        sp[C + c] = shift[c];
+        sp[2 * C + c] = k1;
+        sp[3 * C + c] = -sc * dbeta[c] * inv_n - k1 * mean[c];
+    }
+    __syncthreads();
     const int CG = C >> 3;
     const long long total = (long long)N * H * W * CG;
-    const float inv_n = 1.0f / (float)((long long)N * H * W);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int cg = (int)(idx % CG);
-        const long long p = idx / CG;
-        const int w = (int)(p % W);
-        const int h = (int)((p / W) % H);
-        const int n = (int)(p / ((long long)W * H));
         float g[8], xv[8], r[8];
-        gather_dact<UPSAMPLE>(dout, n, h, w, cg, H, W, C, g);
-        bf8_unpack(*reinterpret_cast<const uint4*>(x + p * C + cg * 8), xv);
+        if (UPSAMPLE) {
+            const long long p = idx / CG;
+            gather_dact<true>(dout, (int)(p / ((long long)W * H)), (int)((p / W) % H), (int)(p % W), cg, H, W, C, g);
+        } else {
+            bf8_unpack(reinterpret_cast<const uint4*>(dout)[idx], g);
+        }
+        bf8_unpack(reinterpret_cast<const uint4*>(x)[idx], xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cg * 8 + j;
-            const float sc = scale[c];
-            const float z = fmaf(xv[j], sc, shift[c]);
+            const float sc = sp[c];
+            const float z = fmaf(xv[j], sc, sp[C + c]);
             const float gj = (relu && z <= 0.f) ? 0.f : g[j];
-            const float xhat = (xv[j] - mean[c]) * rstd[c];
-            r[j] = sc * (gj - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n);
+            r[j] = fmaf(sc, gj, fmaf(sp[2 * C + c], xv[j], sp[3 * C + c]));
         }
-        *reinterpret_cast<uint4*>(dx + idx * 8) = bf8_pack(r);
+        reinterpret_cast<uint4*>(dx)[idx] = bf8_pack(r);
     }
 }
 
@@ -608,11 +660,13 @@ int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const
 int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
                     void* out, cudaStream_t st) {
     KP_REQUIRE(C % 8 == 0, "bn_act_apply: C=%d must be a multiple of 8", C);
-    const long long total = (long long)N * H * W * (C / 8) * (upsample ? 4 : 1);
+    KP_REQUIRE(C <= 4096, "bn_act_apply: C=%d too large", C);
+    const long long total = (long long)N * H * W * (C / 8);     // input vectors (one thread-item each)
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-    if (upsample) bn_act_apply_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(xi, scale, shift, relu, N, H, W, C, o);
-    else bn_act_apply_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(xi, scale, shift, relu, N, H, W, C, o);
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+    if (upsample) bn_act_apply_kernel<true><<<grid_for(total, 256), 256, smem, st>>>(xi, scale, shift, relu, N, H, W, C, o);
+    else bn_act_apply_kernel<false><<<grid_for((total + 1) / 2, 256), 256, smem, st>>>(xi, scale, shift, relu, N, H, W, C, o);
     KP_LAUNCHED();
     return KP_OK;
 }
@@ -626,7 +680,7 @@ int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const flo
     KP_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
     const long long P = (long long)N * H * W;
     const int lanes = 256 / (C / 8);
-    const int rgrid = grid_for((P + lanes - 1) / lanes, 1, 148 * 4);
+    const int rgrid = grid_for((P + 2 * lanes - 1) / (2 * lanes), 1, 148 * 6);
     if (upsample)
         bn_act_bwd_reduce_kernel<true><<<rgrid, 256, 0, st>>>(d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma);
     else
@@ -635,9 +689,9 @@ int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const flo
     const long long total = P * (C / 8);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dx);
     if (upsample)
-        bn_act_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
+        bn_act_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
     else
-        bn_act_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
+        bn_act_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
     KP_LAUNCHED();
     return KP_OK;
 }
@@ -735,6 +789,70 @@ int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t s
     const int lanes = 256 / (C / 8);
     channel_sum_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g),
                                                                                        P, C, out);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+
+}  // namespace kp
+
+// =============================================================================================
+// weight re-layout: fp32 HWIO kernel -> bf16 K-major GEMM operand (one launch per plan; pure data movement + cast)
+//   fwd  : dst[co][t*Kper + kc]  = W[tap_flat[t]][ci(kc)][co] * row_scale[co]   (concat segments padded to CB)
+//   dgrad: dst[ci-c0][t*Kper + co] = W[tap_flat[t]][ci][co]                      (co padded to CB)
+// =============================================================================================
+namespace kp {
+
+__global__ void __launch_bounds__(256)
+pack_weights_fwd_kernel(const float* __restrict__ w, kp_pack_desc d, const float* __restrict__ row_scale,
+                        __nv_bfloat16* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z;
+    const int kc0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const float* wt = w + (long long)d.tap_flat[t] * d.cin * d.cout;
+    // load: rows = kc (source channel), cols = co (contiguous in HWIO)
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int kc = kc0 + i, co = r0 + threadIdx.x;
+        int ci = -1;
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+            if (s < d.nseg && kc >= d.seg_kbase[s] && kc - d.seg_kbase[s] < d.seg_count[s]) ci = d.seg_start[s] + kc - d.seg_kbase[s];
+        tile[i][threadIdx.x] = (ci >= 0 && ci < d.cin && co < d.cout) ? wt[(long long)ci * d.cout + co] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int co = r0 + i, kc = kc0 + threadIdx.x;
+        if (co < d.rows_pad && kc < d.Kper) {
+            float v = tile[threadIdx.x][i];
+            if (row_scale != nullptr && co < d.cout) v *= row_scale[co];
+            dst[(long long)co * d.Ktot + (long long)t * d.Kper + kc] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pack_weights_dgrad_kernel(const float* __restrict__ w, kp_pack_desc d, __nv_bfloat16* __restrict__ dst) {
+    const long long total = (long long)d.rows_pad * d.Ktot;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / d.Ktot);
+        const int k = (int)(idx - (long long)r * d.Ktot);
+        const int t = k / d.Kper, kc = k - t * d.Kper;
+        float v = 0.f;
+        if (r < d.rows && d.c0 + r < d.cin && kc < d.cout) v = w[((long long)d.tap_flat[t] * d.cin + d.c0 + r) * d.cout + kc];
+        dst[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+int ew_pack_weights(const float* w, const kp_pack_desc* d, const float* row_scale, void* dst, cudaStream_t st) {
+    KP_REQUIRE(d->T >= 1 && d->T <= KP_MAX_TAPS && d->Kper > 0 && d->Ktot == d->T * d->Kper, "pack_weights: bad descriptor");
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dst);
+    if (d->mode == 0) {
+        KP_REQUIRE(d->nseg >= 1 && d->nseg <= 3, "pack_weights: 1..3 segments");
+        dim3 grid((unsigned)((d->Kper + 31) / 32), (unsigned)((d->rows_pad + 31) / 32), (unsigned)d->T);
+        pack_weights_fwd_kernel<<<grid, dim3(32, 8), 0, st>>>(w, *d, row_scale, o);
+    } else {
+        const long long total = (long long)d->rows_pad * d->Ktot;
+        pack_weights_dgrad_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, *d, o);
+    }
     KP_LAUNCHED();
     return KP_OK;
 }

@@ -113,6 +113,10 @@ int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float 
     KP_NONNULL(p); KP_NONNULL(g); KP_NONNULL(m); KP_NONNULL(v);
     return ew_adam_tf(p, g, m, v, n, lr, beta1, beta2, eps, t, grad_scale, lr_t_dev, ST);
 }
+int kp_pack_weights(const float* w, const kp_pack_desc* desc, const float* row_scale, void* dst, void* stream) {
+    KP_NONNULL(w); KP_NONNULL(desc); KP_NONNULL(dst);
+    return ew_pack_weights(w, desc, row_scale, dst, ST);
+}
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream) {
     KP_NONNEG(P);
     if (P == 0) return KP_OK;

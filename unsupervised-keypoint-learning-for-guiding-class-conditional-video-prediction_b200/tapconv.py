@@ -301,3 +301,43 @@ def plan_conv_wgrad(x_shape, k, stride, pad, cout, cin_slice=None):
     p.Cin, p.Cout = Cx, cout
     p.dw_off, p.dw_stap, p.dw_sci = c0 * cout, cin_total * cout, cout
     return p
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing descriptor (kp_pack_weights)
+# ------------------------------------------------------------------------------------------------
+class PackDesc(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int), ("T", ctypes.c_int), ("tap_flat", ctypes.c_int * KP_MAX_TAPS),
+                ("cin", ctypes.c_int), ("cout", ctypes.c_int),
+                ("nseg", ctypes.c_int), ("seg_start", ctypes.c_int * 3), ("seg_count", ctypes.c_int * 3),
+                ("seg_kbase", ctypes.c_int * 3),
+                ("c0", ctypes.c_int), ("rows", ctypes.c_int),
+                ("Kper", ctypes.c_int), ("rows_pad", ctypes.c_int), ("Ktot", ctypes.c_int)]
+
+
+def pack_desc(plan, w_shape):
+    """Descriptor of the device weight re-layout for `plan` and an HWIO kernel of shape w_shape (same recipe as
+    pack_weights_np)."""
+    k1, k2, cin, cout = w_shape
+    d = PackDesc()
+    taps = plan.pack["taps"]
+    d.T = len(taps)
+    for i, t in enumerate(taps):
+        d.tap_flat[i] = t
+    d.cin, d.cout = cin, cout
+    d.rows_pad, d.Ktot = plan.rows_pad, plan.Ktot
+    d.Kper = plan.Ktot // len(taps)
+    if plan.pack["mode"] == "fwd":
+        d.mode = 0
+        d.nseg = len(plan.pack["segs"])
+        kb = 0
+        for i, (c_start, c_count) in enumerate(plan.pack["segs"]):
+            d.seg_start[i], d.seg_count[i], d.seg_kbase[i] = c_start, c_count, kb
+            kb += round_up(c_count, plan.CB)
+        assert kb == d.Kper
+    else:
+        d.mode = 1
+        c0, c1 = plan.pack["row_slice"]
+        d.c0, d.rows = c0, c1 - c0
+        assert d.Kper == round_up(cout, plan.CB)
+    return d
