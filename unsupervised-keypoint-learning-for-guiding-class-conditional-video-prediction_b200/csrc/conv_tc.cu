@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
     constexpr uint32_t ROW_BYTES = CB * 2;
     constexpr uint32_t SBO = 8 * ROW_BYTES;
     constexpr uint32_t LAYOUT = (CB == 64) ? 2u : (CB == 32) ? 4u : 6u;
+    // One pipeline stage always carries 64 K-elements: G = 64/CB activation boxes (one per channel block, each with
+    // the swizzle of its own row width) and ONE weight box [BN][64] with the 128-byte swizzle.  For the small-channel
+    // layers (CB 16/32) this divides the barrier round trips of the single-thread TMA / MMA issuers by G.
+    constexpr int G = 64 / CB;
+    constexpr uint32_t A_BOX_BYTES = 128u * CB * 2u;
 
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -134,27 +139,28 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
             for (int m = 0; m < KP_MAX_MAPS; ++m)
                 if (p.nblk[m] > 0) tma_prefetch_desc(&p.mapA[m]);
             tma_prefetch_desc(&p.mapB);
-            uint32_t git = 0;   // ring position, keeps counting across tiles
+            uint32_t git = 0;   // ring position (one per GROUP of G channel blocks), keeps counting across tiles
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
                 const int n_off = nt * p.BN;
-                int it = 0;
-                for (int t = 0; t < p.n_taps; ++t) {
-                    const int cw = w0 + p.dw[t], ch = h0 + p.dh[t];
-                    for (int s = 0; s < p.n_src; ++s) {
+                int t = 0, s = 0, cb = 0;       // (tap, source, channel block) of the next K block
+                for (int it0 = 0; it0 < p.total_iters; it0 += G, ++git) {
+                    const int nv = min(G, p.total_iters - it0);
+                    const uint32_t st = git % (uint32_t)S;
+                    if (git >= (uint32_t)S) mbar_wait(&empty[st], ((git / (uint32_t)S) - 1) & 1);
+                    uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)nv * A_BOX_BYTES + p.b_bytes);
+                    for (int g = 0; g < nv; ++g) {
                         const int m = p.mf[t] + s;
-                        const int nb = p.nblk[m];
-                        for (int cb = 0; cb < nb; ++cb, ++it, ++git) {
-                            const uint32_t st = git % (uint32_t)S;
-                            if (git >= (uint32_t)S) mbar_wait(&empty[st], ((git / (uint32_t)S) - 1) & 1);
-                            uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
-                            mbar_arrive_expect_tx(&full[st], p.a_bytes + p.b_bytes);
-                            tma_load_4d(a_dst, &p.mapA[m], &full[st], cb * CB, cw, ch, n0);
-                            tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it * CB, n_off);
+                        tma_load_4d(a_dst + (size_t)g * A_BOX_BYTES, &p.mapA[m], &full[st], cb * CB, w0 + p.dw[t], h0 + p.dh[t], n0);
+                        if (++cb == p.nblk[m]) {
+                            cb = 0;
+                            if (++s == p.n_src) { s = 0; ++t; }
                         }
                     }
+                    tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it0 * CB, n_off);   // [BN][64] K-major, 128B swizzle
                 }
             }
         }
@@ -169,17 +175,22 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 if (lt >= 2) mbar_wait(&tempty[acc], ((lt >> 1) - 1) & 1);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * p.BN);
-                for (int it = 0; it < p.total_iters; ++it, ++git) {
+                for (int it0 = 0; it0 < p.total_iters; it0 += G, ++git) {
+                    const int nv = min(G, p.total_iters - it0);
                     const uint32_t st = git % (uint32_t)S;
                     mbar_wait(&full[st], (git / (uint32_t)S) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + st * p.stage_bytes;
                     const uint32_t b_addr = a_addr + p.a_bytes;
+                    for (int g = 0; g < nv; ++g) {
 #pragma unroll
-                    for (int k = 0; k < CB / 16; ++k) {
-                        const uint64_t da = umma_smem_desc(a_addr + k * 32, SBO, 16, LAYOUT);
-                        const uint64_t db = umma_smem_desc(b_addr + k * 32, SBO, 16, LAYOUT);
-                        umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < CB / 16; ++k) {
+                            // A: box g, rows of CB*2 bytes with the matching swizzle; B: 128-byte rows (64 K-elements),
+                            // the 16-element slice of block g / step k sits (g*CB + k*16)*2 bytes into the row
+                            const uint64_t da = umma_smem_desc(a_addr + g * A_BOX_BYTES + k * 32, SBO, 16, LAYOUT);
+                            const uint64_t db = umma_smem_desc(b_addr + (g * CB + k * 16) * 2, 1024, 16, 2u);
+                            umma_bf16(d_tmem, da, db, idesc, (it0 | g | k) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty[st]);
                 }
@@ -456,10 +467,10 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
         KP_REQUIRE((reinterpret_cast<uintptr_t>(wpacked) & 15) == 0, "kp_tapconv: packed weights not 16-byte aligned");
         cuuint64_t gdim[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Cout_pad};
         cuuint64_t gstr[1] = {(cuuint64_t)d->Ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)CB, (cuuint32_t)BN};
+        cuuint32_t box[2] = {64u, (cuuint32_t)BN};     // 64 K-elements (G channel blocks) per stage, 128-byte rows
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("kp_tapconv: cuTensorMapEncodeTiled(weights) failed with %d (Ktot=%d Cout_pad=%d)", (int)r, d->Ktot,
@@ -478,8 +489,8 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.total_tiles = p.tiles_w * p.tiles_h * tiles_n * p.n_tiles;
     p.tmem_cols = pow2_at_least(2 * BN, 32);          // double-buffered accumulator
     p.total_iters = total_iters;
-    p.a_bytes = 128u * CB * 2u;
-    p.b_bytes = (uint32_t)BN * CB * 2u;
+    p.a_bytes = 128u * 64u * 2u;                       // G = 64/CB activation boxes of 128 x CB
+    p.b_bytes = (uint32_t)BN * 64u * 2u;               // one weight box [BN][64]
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
     // CTAs per SM: two independent pipelines per SM hide the barrier round trips of the single-thread TMA / MMA
     // issuers; the 256-wide tiles need all 512 TMEM columns and most of the shared memory, so they run alone.
