@@ -186,6 +186,15 @@ int kp_image_prep(const float* x, long long P, const float* a, const float* b, c
 /* its adjoint: g bf16 [P,16] -> dx f32 [P,3] (accumulate != 0: +=). */
 int kp_image_prep_bwd(const void* g, long long P, const float* a, const int* perm, int accumulate, float* dx, void* stream);
 
+/* W-unrolled variant for the 3-channel first layers (encoder conv_1 7x7, models/networks/__init__.py:10; VGG conv1_1,
+ * models/networks/vgg.py:20): out bf16 [N,H,W,Cpad], out[n,h,w,kw*3+c] = a[c]*x[n,h,w+kw-pad_left,perm[c]] + b[c]
+ * (0 outside the image, Cpad in {16,32}).  A KHxKW conv over 3 channels then is a KHx1 conv over KW*3 channels with
+ * the HWIO kernel reinterpreted in place as [KH][1][KW*3][Cout] (KH taps instead of KH*KW).  _bwd is the adjoint.  */
+int kp_image_prep_unrolled(const float* x, int N, int H, int W, int KW, int pad_left, int Cpad, const float* a,
+                           const float* b, const int* perm, void* out, void* stream);
+int kp_image_prep_unrolled_bwd(const void* g, int N, int H, int W, int KW, int pad_left, int Cpad, const float* a,
+                               const int* perm, int accumulate, float* dx, void* stream);
+
 /* tf.contrib.layers.batch_norm (models/networks/layers.py:13-14), training mode, split around the convolution:
  * the conv epilogue accumulates per-channel sum / sum-of-squares of its PRE-bias accumulators
  * (kp_tapconv_bf16 stats_*); kp_bn_finalize turns them into scale/shift (normalising with the biased
@@ -199,10 +208,12 @@ int kp_bn_finalize(const float* stats_sum, const float* stats_sq, const float* c
 int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W,
                     int C, void* out, void* stream);
 /* backward of kp_bn_act_apply + batch-norm statistics: dout (grad of the output, upsampled size if upsample),
- * x (the conv output saved by the forward) -> dbeta, dgamma f32 [C] and dx bf16 [N,H,W,C].            */
+ * x (the conv output saved by the forward) -> dbeta, dgamma f32 [C] (this call's sums; zeroed by the library
+ * unless prezeroed != 0) and dx bf16 [N,H,W,C].  gbeta_acc / ggamma_acc (nullable): parameter-gradient buffers
+ * that additionally receive += dbeta / dgamma.                                                          */
 int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
                   const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, void* stream);
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, void* stream);
 /* g = dy * (y > 0 ? 1 : alpha): backward of the fused bias+ReLU / bias+leaky_relu epilogues. */
 int kp_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, void* stream);
 /* tf.nn.max_pool 2x2 s2 (models/networks/vgg.py:45-46) and its backward (gradient to the first maximum; with

@@ -26,12 +26,12 @@ def conv2d(x, kernel, bias=None, stride=1, pad=0):
 
     x [B,H,W,Cin]; kernel HWIO [k,k,Cin,Cout]; bias [Cout] or None.
     """
-    k = kernel.shape[0]
+    kh, kw = kernel.shape[0], kernel.shape[1]
     xc = x.permute(0, 3, 1, 2)
     if pad:
         xc = F.pad(xc, (pad, pad, pad, pad))
-    pt, pb = same_pad(xc.shape[2], k, stride)
-    pl, pr = same_pad(xc.shape[3], k, stride)
+    pt, pb = same_pad(xc.shape[2], kh, stride)
+    pl, pr = same_pad(xc.shape[3], kw, stride)
     xc = F.pad(xc, (pl, pr, pt, pb))
     y = F.conv2d(xc, kernel.permute(3, 2, 0, 1).contiguous(), bias, stride=stride)
     return y.permute(0, 2, 3, 1)

@@ -326,3 +326,49 @@ def test_pack_weights_kernel_matches_recipe(cuda_dev):
                 ref_d = torch.from_numpy(tc.pack_weights_np(p, w)).to(torch.bfloat16)
                 assert torch.equal(conv.pack_weights(p, wd).cpu(), ref_d)
             c0 += sh[3]
+
+
+@pytest.mark.parametrize("k,cpad,cout,with_bn", [(7, 32, 32, True), (3, 16, 64, False)])
+def test_w_unrolled_first_layer_matches_square_conv(cuda_dev, k, cpad, cout, with_bn):
+    """The 3-channel first layers run as k x 1 convolutions over a W-unrolled image (kp_image_prep_unrolled): forward,
+    weight gradient (written straight into the [k,k,3,cout] variable) and image gradient must equal the k x k conv."""
+    from kp_b200 import engine as E, ops, tapconv as tc
+    rng = np.random.default_rng(k)
+    N, H, W = 2, 24, 20
+    img = torch.from_numpy(rng.uniform(-1, 1, (N, H, W, 3)).astype(np.float32))
+    w = torch.from_numpy((rng.normal(size=(k, k, 3, cout)) / np.sqrt(k * k * 3)).astype(np.float32)).to(BF).float()
+    b = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32))
+    ctx = _mk_ctx(cuda_dev, {"t/conv2d/kernel": w, "t/conv2d/bias": b}, {"bn": cout} if with_bn else None)
+    if with_bn:
+        ctx.G.p("bn/gamma").fill_(1.0)
+        ctx.S.p("bn/moving_variance").fill_(1.0)
+    ctx.tape, ctx.train_G = E.Tape(), True
+    prep = ops.VGG_PREP if not with_bn else ops.IDENT_PREP
+    imd = img.to(cuda_dev)
+    xp = ops.image_prep_unrolled(imd, k, (k - 1) // 2, cpad, prep)
+    y = E.conv_layer(ctx, [xp], "t/conv2d/kernel", "t/conv2d/bias", (k, 1), 1, 0, bn="bn" if with_bn else None,
+                     train_mode=with_bn, act=tc.ACT_NONE if with_bn else tc.ACT_RELU, wshape=(k, 1, 3 * k, cout))
+    # oracle: the square conv on the bf16-rounded preprocessed image
+    a_, b_, perm = prep
+    pre_img = torch.stack([img[..., perm[c]] * a_[c] + b_[c] for c in range(3)], dim=-1).to(BF).double().requires_grad_(True)
+    w64 = w.double().requires_grad_(True)
+    z = T.conv2d(pre_img, w64, b.double(), 1, 0)
+    if with_bn:
+        z, _, _ = T.batch_norm(z, torch.ones(cout, dtype=torch.float64), torch.zeros(cout, dtype=torch.float64),
+                               torch.zeros(cout, dtype=torch.float64), torch.ones(cout, dtype=torch.float64), True)
+    ref = torch.relu(z)
+    _close(y, ref.detach(), 1e-2, "forward")
+    dout = torch.from_numpy(rng.normal(size=tuple(y.shape)).astype(np.float32)).to(BF)
+    ctx.tape.set_grad(y, dout.to(cuda_dev))
+    ref.backward(dout.double())
+    for fn in reversed(ctx.tape.ops):
+        fn()
+    _close(ctx.G.g("t/conv2d/kernel"), w64.grad, 1e-2, "dW")
+    # image gradient through the adjoint of the unrolling (and of the affine preprocessing)
+    g = ctx.tape.grad(xp)
+    dimg = torch.zeros_like(imd)
+    ops.image_prep_unrolled_bwd(g, dimg, k, (k - 1) // 2, prep)
+    ref_dimg = torch.zeros_like(img, dtype=torch.float64)
+    for c in range(3):
+        ref_dimg[..., perm[c]] += pre_img.grad[..., c] * a_[c]
+    _close(dimg, ref_dimg, 1.5e-2, "d_image")

@@ -39,7 +39,7 @@ SIGNATURES = {
                        c_vp, c_vp, c_vp],
     "kp_bn_act_apply": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
-                      c_vp],
+                      c_vp, c_vp, c_int, c_vp],
     "kp_act_mask_bwd": [c_vp, c_vp, c_float, c_ll, c_vp, c_vp],
     "kp_maxpool2x2_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_maxpool2x2_bwd": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
@@ -52,6 +52,8 @@ SIGNATURES = {
     "kp_adam_tf": [c_vp, c_vp, c_vp, c_vp, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, c_vp, c_vp],
     "kp_channel_sum": [c_vp, c_ll, c_int, c_vp, c_vp],
     "kp_pack_weights": [c_vp, c_vp, c_vp, c_vp, c_vp],
+    "kp_image_prep_unrolled": [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "kp_image_prep_unrolled_bwd": [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
 }
 _RESTYPES = {"kp_last_error": ctypes.c_char_p, "kp_launch_count": ctypes.c_ulonglong}
 

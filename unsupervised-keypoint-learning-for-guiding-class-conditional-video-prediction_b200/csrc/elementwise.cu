@@ -301,8 +301,16 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ dbeta, const float* __restrict__ dgamma,
-                        int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+                        int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ dx,
+                        float* __restrict__ gbeta_acc, float* __restrict__ ggamma_acc) {
     extern __shared__ float sp[];   // [4][C]: sc, sh, k1, k0
+    if (blockIdx.x == 0 && gbeta_acc != nullptr) {
+        // fold this call's dbeta / dgamma into the parameter-gradient buffers (the shared pose_encoder accumulates two calls)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            gbeta_acc[c] += dbeta[c];
+            ggamma_acc[c] += dgamma[c];
+        }
+    }
     const float inv_n = 1.0f / (float)((long long)N * H * W);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float sc = scale[c];
@@ -672,12 +680,14 @@ int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int r
 }
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
                   const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, cudaStream_t st) {
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, cudaStream_t st) {
     KP_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_act_bwd: C=%d must be 8 x a power of two <= 2048", C);
     const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dout);
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
-    KP_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
-    KP_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
+    if (!prezeroed) {
+        KP_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
+        KP_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
+    }
     const long long P = (long long)N * H * W;
     const int lanes = 256 / (C / 8);
     const int rgrid = grid_for((P + 2 * lanes - 1) / (2 * lanes), 1, 148 * 6);
@@ -689,9 +699,9 @@ int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const flo
     const long long total = P * (C / 8);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dx);
     if (upsample)
-        bn_act_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
+        bn_act_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc);
     else
-        bn_act_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o);
+        bn_act_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc);
     KP_LAUNCHED();
     return KP_OK;
 }
@@ -853,6 +863,97 @@ int ew_pack_weights(const float* w, const kp_pack_desc* d, const float* row_scal
         const long long total = (long long)d->rows_pad * d->Ktot;
         pack_weights_dgrad_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, *d, o);
     }
+    KP_LAUNCHED();
+    return KP_OK;
+}
+
+}  // namespace kp
+
+// =============================================================================================
+// W-unrolled image packing for 3-channel first layers (encoder conv_1 7x7, VGG conv1_1 3x3):
+//   out[n,h,w, kw*3 + c] = a[c]*x[n,h,w+kw-pl,perm[c]] + b[c]   (0 outside the image; channels KW*3.. zero)
+// A KHxKW convolution over 3 channels becomes a KHx1 convolution over KW*3 channels of this tensor: KH taps of
+// 32-64 bytes instead of KH*KW taps of 6 bytes, with the HWIO kernel [KH][KW][3][Cout] reinterpreted in place as
+// [KH][1][KW*3][Cout].  The zero fill happens AFTER the affine map (TF pads the already-preprocessed image).
+// =============================================================================================
+namespace kp {
+
+template <int CPAD>
+__global__ void __launch_bounds__(256)
+image_prep_unrolled_kernel(const float* __restrict__ x, int N, int H, int W, int KW, int pl, ImgPrep q,
+                           __nv_bfloat16* __restrict__ out) {
+    const long long P = (long long)N * H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(p % W);
+        const long long row = p - w;     // first pixel of this image row
+        float f[CPAD];
+#pragma unroll
+        for (int i = 0; i < CPAD; ++i) f[i] = 0.f;
+#pragma unroll
+        for (int kw = 0; kw < CPAD / 3; ++kw) {
+            if (kw < KW) {
+                const int ws = w + kw - pl;
+                if (ws >= 0 && ws < W) {
+                    const float* px = x + 3 * (row + ws);
+                    const float in[3] = {px[0], px[1], px[2]};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) f[kw * 3 + c] = fmaf(q.a[c], in[q.perm[c]], q.b[c]);
+                }
+            }
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + CPAD * p);
+#pragma unroll
+        for (int v = 0; v < CPAD / 8; ++v) o[v] = bf8_pack(f + 8 * v);
+    }
+}
+
+// adjoint: g bf16 [N,H,W,CPAD] -> dx f32 [N,H,W,3]: dx[n,h,w',perm[c]] (+)= a[c] * sum_kw g[n,h,w'-kw+pl, kw*3+c]
+template <int CPAD>
+__global__ void __launch_bounds__(256)
+image_prep_unrolled_bwd_kernel(const __nv_bfloat16* __restrict__ g, int N, int H, int W, int KW, int pl, ImgPrep q,
+                               int accumulate, float* __restrict__ dx) {
+    const long long P = (long long)N * H * W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(p % W);
+        const long long row = p - w;
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int kw = 0; kw < KW; ++kw) {
+            const int wd = w - kw + pl;
+            if (wd < 0 || wd >= W) continue;
+            const __nv_bfloat16* gp = g + CPAD * (row + wd) + kw * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] += __bfloat162float(gp[c]);
+        }
+        float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[q.perm[c]] = q.a[c] * acc[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dx[3 * p + c] = accumulate ? dx[3 * p + c] + o[c] : o[c];
+    }
+}
+
+int ew_image_prep_unrolled(const float* x, int N, int H, int W, int KW, int pl, int cpad, const float* a, const float* b,
+                           const int* perm, void* out, cudaStream_t st) {
+    KP_REQUIRE(KW >= 1 && KW * 3 <= cpad && (cpad == 16 || cpad == 32), "image_prep_unrolled: KW*3 must fit Cpad in {16,32}");
+    ImgPrep q;
+    for (int c = 0; c < 3; ++c) { q.a[c] = a[c]; q.b[c] = b[c]; q.perm[c] = perm[c]; }
+    const long long P = (long long)N * H * W;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (cpad == 16) image_prep_unrolled_kernel<16><<<grid_for(P, 256), 256, 0, st>>>(x, N, H, W, KW, pl, q, o);
+    else image_prep_unrolled_kernel<32><<<grid_for(P, 256), 256, 0, st>>>(x, N, H, W, KW, pl, q, o);
+    KP_LAUNCHED();
+    return KP_OK;
+}
+
+int ew_image_prep_unrolled_bwd(const void* g, int N, int H, int W, int KW, int pl, int cpad, const float* a, const int* perm,
+                               int accumulate, float* dx, cudaStream_t st) {
+    KP_REQUIRE(KW >= 1 && KW * 3 <= cpad && (cpad == 16 || cpad == 32), "image_prep_unrolled_bwd: KW*3 must fit Cpad in {16,32}");
+    ImgPrep q;
+    for (int c = 0; c < 3; ++c) { q.a[c] = a[c]; q.b[c] = 0.f; q.perm[c] = perm[c]; }
+    const long long P = (long long)N * H * W;
+    const __nv_bfloat16* gi = reinterpret_cast<const __nv_bfloat16*>(g);
+    if (cpad == 16) image_prep_unrolled_bwd_kernel<16><<<grid_for(P, 256), 256, 0, st>>>(gi, N, H, W, KW, pl, q, accumulate, dx);
+    else image_prep_unrolled_bwd_kernel<32><<<grid_for(P, 256), 256, 0, st>>>(gi, N, H, W, KW, pl, q, accumulate, dx);
     KP_LAUNCHED();
     return KP_OK;
 }

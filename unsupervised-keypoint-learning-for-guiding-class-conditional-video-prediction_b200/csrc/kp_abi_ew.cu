@@ -43,11 +43,13 @@ int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int r
 }
 int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
                   const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, void* stream) {
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, void* stream) {
     KP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", __func__);
     KP_NONNULL(dout); KP_NONNULL(x); KP_NONNULL(scale); KP_NONNULL(shift); KP_NONNULL(save_mean); KP_NONNULL(save_rstd);
     KP_NONNULL(dbeta); KP_NONNULL(dgamma); KP_NONNULL(dx);
-    return ew_bn_act_bwd(dout, x, scale, shift, save_mean, save_rstd, relu, upsample, N, H, W, C, dbeta, dgamma, dx, ST);
+    KP_REQUIRE((gbeta_acc == nullptr) == (ggamma_acc == nullptr), "%s: gbeta_acc and ggamma_acc go together", __func__);
+    return ew_bn_act_bwd(dout, x, scale, shift, save_mean, save_rstd, relu, upsample, N, H, W, C, dbeta, dgamma, dx, gbeta_acc,
+                         ggamma_acc, prezeroed, ST);
 }
 int kp_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, void* stream) {
     KP_NONNEG(n_elems);
@@ -125,3 +127,20 @@ int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream) 
 }
 
 }  // extern "C"
+
+extern "C" int kp_image_prep_unrolled(const float* x, int N, int H, int W, int KW, int pad_left, int Cpad, const float* a,
+                                      const float* b, const int* perm, void* out, void* stream) {
+    KP_REQUIRE(N >= 0 && H > 0 && W > 0, "%s: bad shape", __func__);
+    if (N == 0) return KP_OK;
+    KP_NONNULL(x); KP_NONNULL(a); KP_NONNULL(b); KP_NONNULL(perm); KP_NONNULL(out);
+    for (int c = 0; c < 3; ++c) KP_REQUIRE(perm[c] >= 0 && perm[c] < 3, "%s: perm out of range", __func__);
+    return ew_image_prep_unrolled(x, N, H, W, KW, pad_left, Cpad, a, b, perm, out, ST);
+}
+extern "C" int kp_image_prep_unrolled_bwd(const void* g, int N, int H, int W, int KW, int pad_left, int Cpad, const float* a,
+                                          const int* perm, int accumulate, float* dx, void* stream) {
+    KP_REQUIRE(N >= 0 && H > 0 && W > 0, "%s: bad shape", __func__);
+    if (N == 0) return KP_OK;
+    KP_NONNULL(g); KP_NONNULL(a); KP_NONNULL(perm); KP_NONNULL(dx);
+    for (int c = 0; c < 3; ++c) KP_REQUIRE(perm[c] >= 0 && perm[c] < 3, "%s: perm out of range", __func__);
+    return ew_image_prep_unrolled_bwd(g, N, H, W, KW, pad_left, Cpad, a, perm, accumulate, dx, ST);
+}

@@ -36,7 +36,7 @@ int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int r
                     void* out, cudaStream_t st);
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
                   const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, cudaStream_t st);
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, cudaStream_t st);
 int ew_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, cudaStream_t st);
 int ew_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, cudaStream_t st);
 int ew_maxpool_bwd(const void* dy, const void* x, int relu_mask, int N, int H, int W, int C, void* dx, cudaStream_t st);
@@ -54,5 +54,9 @@ int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float 
                float grad_scale, const float* lr_t_dev, cudaStream_t st);
 int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st);
 int ew_pack_weights(const float* w, const kp_pack_desc* d, const float* row_scale, void* dst, cudaStream_t st);
+int ew_image_prep_unrolled(const float* x, int N, int H, int W, int KW, int pl, int cpad, const float* a, const float* b,
+                           const int* perm, void* out, cudaStream_t st);
+int ew_image_prep_unrolled_bwd(const void* g, int N, int H, int W, int KW, int pl, int cpad, const float* a, const int* perm,
+                               int accumulate, float* dx, cudaStream_t st);
 
 }  // namespace kp

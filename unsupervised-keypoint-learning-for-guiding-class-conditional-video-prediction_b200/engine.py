@@ -113,8 +113,30 @@ class Context:
         self.train_D = False                          # accumulate img_discr weight gradients
         self.train_G = False
         self.debug = None                             # dict: layer scope -> internals (tests / probes only)
+        self.zpool = None
+        self.zoff = 0
         self._plans = {}
         self._packed = {}
+
+    # ---- pooled zero-initialised scratch (BN statistics, per-call gradient sums): ONE memset per run ----
+    ZPOOL_FLOATS = 4 * 1024 * 1024
+
+    def begin_run(self):
+        """Call at the start of every forward(/backward) run: re-zeroes the scratch pool with a single memset."""
+        if self.zpool is None:
+            self.zpool = torch.zeros(self.ZPOOL_FLOATS, device=self.device, dtype=F32)
+        else:
+            self.zpool[:max(self.zoff, 1)].zero_()
+        self.zoff = 0
+
+    def zeros(self, n):
+        """n zeroed floats valid until the next begin_run() (falls back to torch.zeros when the pool is exhausted)."""
+        n4 = (n + 3) // 4 * 4
+        if self.zpool is None or self.zoff + n4 > self.zpool.numel():
+            return torch.zeros(n, device=self.device, dtype=F32)
+        out = self.zpool[self.zoff:self.zoff + n]
+        self.zoff += n4
+        return out
 
     # ---- parameter lookup ----
     def group_of(self, name):
@@ -171,10 +193,12 @@ class Context:
 # --------------------------------------------------------------------------------------------------
 # convolution layer (+ BN / activation), forward and tape entry
 # --------------------------------------------------------------------------------------------------
-def _conv_weights(ctx, wnames):
-    """HWIO kernel of the layer; several TF variables may be fused along Cout (translator heads)."""
+def _conv_weights(ctx, wnames, wshape=None):
+    """HWIO kernel of the layer; several TF variables may be fused along Cout (translator heads).  `wshape`
+    reinterprets the (contiguous) variable in place, e.g. [7,7,3,32] as [7,1,21,32] for the W-unrolled first layer."""
     if len(wnames) == 1:
-        return ctx.p(wnames[0])
+        w = ctx.p(wnames[0])
+        return w if wshape is None else w.view(wshape)
     return torch.cat([ctx.p(n) for n in wnames], dim=3)
 
 
@@ -187,7 +211,7 @@ def _bias_vec(ctx, bnames, rows_pad):
 
 
 def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode=False, act=tc.ACT_NONE, alpha=0.0,
-               upsample=False, out_f32=False, need_input_grad=True, stats_prefix=None):
+               upsample=False, out_f32=False, need_input_grad=True, wshape=None):
     """layers.conv [+ layers.batch_norm + relu] [+ resize x2] of the reference, on bf16 NHWC tensors.
 
     srcs: list of bf16 [N,H,W,C] tensors (virtual channel concat).  Returns the layer output (bf16, or f32 when
@@ -199,8 +223,9 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
     if isinstance(bnames, str):
         bnames = [bnames]
     shapes = tuple(tuple(s.shape) for s in srcs)
-    w = _conv_weights(ctx, wnames)
+    w = _conv_weights(ctx, wnames, wshape)
     cout = w.shape[3]
+    cin_real = w.shape[2]
     cin_src = sum(s[3] for s in shapes)
     flop_scale = w.shape[2] / float(cin_src)      # algorithmic-FLOP accounting ignores zero-padded channels
     if cin_src > w.shape[2]:
@@ -231,8 +256,8 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
 
     if bn is not None:
         # training-mode BN: conv (+bias) with statistics in the epilogue -> finalize -> normalise + ReLU (+ x2)
-        ssum = torch.zeros(fplan.rows_pad, device=dev, dtype=F32)
-        ssq = torch.zeros(fplan.rows_pad, device=dev, dtype=F32)
+        ssum = ctx.zeros(fplan.rows_pad)
+        ssq = ctx.zeros(fplan.rows_pad)
         y_pre = torch.empty((N, Ho, Wo, cout), device=dev, dtype=BF16)
         cv.run_plan(fplan, srcs, wp, bias, y_pre, act=tc.ACT_NONE, stats=(ssum, ssq))
         mm = ctx.p(bn + "/moving_mean") if ctx.update_moving else None
@@ -249,10 +274,13 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
                 dout = tape.grad(out)
                 if dout is None:
                     return
-                dy, dgamma, dbeta = ops.bn_act_bwd(dout, y_pre, scale, shift, mean, rstd, relu=True, upsample=upsample)
-                group.g(bn + "/gamma").add_(dgamma)
-                group.g(bn + "/beta").add_(dbeta)
-                _conv_backward(ctx, tape, srcs, shapes, wnames, None, w, k, stride, pad, cout, dy, group, need_input_grad)
+                train = (group is ctx.G and ctx.train_G) or (group is ctx.D and ctx.train_D)
+                dy, _, _ = ops.bn_act_bwd(dout, y_pre, scale, shift, mean, rstd, relu=True, upsample=upsample,
+                                          gbeta_acc=group.g(bn + "/beta") if train else None,
+                                          ggamma_acc=group.g(bn + "/gamma") if train else None,
+                                          zeroed=ctx.zeros(2 * cout))
+                _conv_backward(ctx, tape, srcs, shapes, wnames, None, w, k, stride, pad, cout, dy, group, need_input_grad,
+                               cin_real, wshape)
             tape.record(bwd)
         return out
 
@@ -270,23 +298,26 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
                 dy = ops.act_mask_bwd(dy, y, 0.0)
             elif act == tc.ACT_LEAKY:
                 dy = ops.act_mask_bwd(dy, y, alpha)
-            _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad)
+            _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad,
+                           cin_real, wshape)
         tape.record(bwd)
     return y
 
 
-def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad):
+def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad,
+                           cin_real, wshape):
     """dy: bf16 gradient w.r.t. the convolution output, [N,Ho,Wo,cpad] with cpad = round_up(cout, 8)."""
     cpad = dy.shape[3]
     train = group.trainable and ((group is ctx.G and ctx.train_G) or (group is ctx.D and ctx.train_D))
     cin = sum(s[3] for s in shapes)
     if train:
-        cin_real = ctx.p(wnames[0]).shape[2]
+        k_h, k_w = tc._khw(k)
+        gview = (lambda n: group.g(n)) if wshape is None else (lambda n: group.g(n).view(wshape))
         direct = cpad == cout and len(wnames) == 1 and cin_real == cin
         if direct:
-            gw = group.g(wnames[0])
+            gw = gview(wnames[0])
         else:
-            gw = torch.zeros((k, k, cin, cpad), device=ctx.device, dtype=F32)
+            gw = ctx.zeros(k_h * k_w * cin * cpad).view(k_h, k_w, cin, cpad)
         c0 = 0
         for s, shp in zip(srcs, shapes):
             C = shp[3]
@@ -299,10 +330,10 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
             o = 0
             for n in wnames:
                 co = ctx.p(n).shape[3]
-                group.g(n).add_(gw[:, :, :cin_real, o:o + co])
+                gview(n).add_(gw[:, :, :cin_real, o:o + co])
                 o += co
         if bnames:
-            gb = torch.zeros(cpad, device=ctx.device, dtype=F32)
+            gb = ctx.zeros(cpad)
             ops.channel_sum(dy, gb)
             o = 0
             for n in bnames:
@@ -319,7 +350,7 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
                          lambda shp=shp, c0=c0, C=C: tc.plan_conv_dgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
         dx, acc = tape.acquire(s)
         for i, p in enumerate(plans):
-            p.flop_scale = (ctx.p(wnames[0]).shape[2] / float(cin)) * (cout / float(cpad))
+            p.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
             wp = ctx.packed(("dgrad", tuple(wnames), shp, c0, cpad, i), lambda p=p: cv.pack_weights(p, wpad))
             cv.run_plan(p, [dy], wp, None, dx, accumulate=acc)
         c0 += C

@@ -118,7 +118,7 @@ class DetectorTranslatorModel(BaseModel):
         networks.set_context(self.ctx)
         tm = self.is_training
         embeddings = networks.image_encoder(im, tm) if for_G_run else \
-            [im] + networks.encoder(networks._prep(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
+            [im] + networks.encoder(networks._prep7(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
         current_gauss_pt, current_pt_map = networks.pose_encoder_with_maps(im, self.n_points, tm, (32, 32))
         future_gauss_pt, future_pt_map = networks.pose_encoder_with_maps(future_im, self.n_points, tm, (32, 32))
         joint_embedding = networks.joint_embedding(embeddings[-2], current_pt_map, future_pt_map)
@@ -158,9 +158,10 @@ class DetectorTranslatorModel(BaseModel):
         loss = torch.zeros(2, device=self.device)             # [reconstruction, adversarial]
         tape = ctx.tape
         ctx.tape = None
-        feat_gt = networks.vgg.features_from_prepared(ops.image_prep(future_im, ops.VGG_PREP), need_input_grad=False)
+        feat_gt = networks.vgg.features_from_prepared(networks.vgg.prepare(future_im, ops.VGG_PREP), need_input_grad=False)
         ctx.tape = tape
-        xp = networks._prep_with_grad(ctx, future_im_pred, ops.VGG_PREP) if backward else ops.image_prep(future_im_pred, ops.VGG_PREP)
+        xp = networks._prep_with_grad(ctx, future_im_pred, ops.VGG_PREP, networks.vgg.VGG_UNROLL) if backward else \
+            networks.vgg.prepare(future_im_pred, ops.VGG_PREP)
         feat_pred = networks.vgg.features_from_prepared(xp, need_input_grad=backward)
         for fg, fp in zip(feat_gt, feat_pred):
             d = torch.empty_like(fp) if backward else None
@@ -180,6 +181,7 @@ class DetectorTranslatorModel(BaseModel):
     # ---- the two runs of one train step ----
     def _run_D(self, im, future_im):
         ctx = self.ctx
+        ctx.begin_run()
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = None, False, False, False
         fake = self._define_forward_pass(im, future_im, for_G_run=False)
         ctx.tape, ctx.train_D = E.Tape(), True
@@ -196,6 +198,7 @@ class DetectorTranslatorModel(BaseModel):
 
     def _run_G(self, im, future_im):
         ctx = self.ctx
+        ctx.begin_run()
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = E.Tape(), True, True, False
         ctx.G.grad.zero_()
         fake = self._define_forward_pass(im, future_im, for_G_run=True)
@@ -280,6 +283,7 @@ class DetectorTranslatorModel(BaseModel):
         ctx = self.ctx
         start_time = time.time()
         im, fut = self._next_batch(feed_dict)
+        ctx.begin_run()
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = None, False, False, False
         fake = self._define_forward_pass(im, fut, for_G_run=False)
         lD = self._compute_loss_D(fake, fut, backward=False)

@@ -112,19 +112,28 @@ def _prep(x):
     return ops.image_prep(x)
 
 
+def _prep7(x):
+    """Encoder input: float32 NHWC image -> W-unrolled bf16 [B,H,W,32] (7 horizontal taps x 3 channels, SAME pad 3),
+    so that the 7x7x3 conv_1 runs as a 7x1 convolution over 21 channels (7 taps instead of 49)."""
+    if x.dtype == torch.bfloat16:
+        return x
+    return ops.image_prep_unrolled(x, 7, 3, 32)
+
+
 def _cbr(ctx, srcs, conv_scope, bn_scope, train_mode, k=3, stride=1, upsample=False, need_input_grad=True):
     return E.conv_layer(ctx, srcs, conv_scope + "/conv2d/kernel", conv_scope + "/conv2d/bias", k, stride, 0, bn=bn_scope,
                         train_mode=train_mode, upsample=upsample, need_input_grad=need_input_grad)
 
 
 def encoder(x, train_mode, filters=32, _scope="encoder/", _n_blocks=4):
-    """reference networks/__init__.py:7-26.  x: prepared bf16 image.  Returns the 4 block features (bf16).
+    """reference networks/__init__.py:7-26.  x: prepared (W-unrolled, see _prep7) bf16 image.  Returns the 4 block features.
     `_n_blocks=3` skips conv_7/conv_8, whose output the stage-1 graph never consumes: TF prunes
     them from the D run; the G run still executes them for their moving-average updates."""
     ctx = get_context()
     p = _scope
     block_features = []
-    x = _cbr(ctx, [x], p + "conv_1", p + "b_norm_1", train_mode, k=7, need_input_grad=False)
+    x = E.conv_layer(ctx, [x], p + "conv_1/conv2d/kernel", p + "conv_1/conv2d/bias", (7, 1), 1, 0, bn=p + "b_norm_1",
+                     train_mode=train_mode, need_input_grad=False, wshape=(7, 1, 21, filters))
     x = _cbr(ctx, [x], p + "conv_2", p + "b_norm_2", train_mode)
     block_features.append(x)
     for i in range(_n_blocks - 1):
@@ -136,13 +145,13 @@ def encoder(x, train_mode, filters=32, _scope="encoder/", _n_blocks=4):
 
 def image_encoder(x, train_mode):
     """reference networks/__init__.py:29-33: returns [x] + block features; consumers use [-2] (32x32x128)."""
-    return [x] + encoder(_prep(x), train_mode, _scope="image_encoder/encoder/")
+    return [x] + encoder(_prep7(x), train_mode, _scope="image_encoder/encoder/")
 
 
 def pose_encoder_logits(x, n_pts, train_mode, final_res=128, filters=128):
     """Everything of pose_encoder before get_coord (reference networks/__init__.py:36-66): fp32 logits [B,128,128,n_pts]."""
     ctx = get_context()
-    block_features = encoder(_prep(x), train_mode, _scope="pose_encoder/encoder/")
+    block_features = encoder(_prep7(x), train_mode, _scope="pose_encoder/encoder/")
     x = block_features[-1]
     size = x.shape[1]
     conv_id = 1
@@ -261,9 +270,10 @@ def compose(im, heads, clip=False, want_parts=False):
     return (final, crude, mask) if want_parts else final
 
 
-def _prep_with_grad(ctx, x, prep):
-    """image_prep of a tensor that needs a gradient (the generated frame entering VGG / the discriminator)."""
-    xp = ops.image_prep(x, prep)
+def _prep_with_grad(ctx, x, prep, unroll=None):
+    """image_prep of a tensor that needs a gradient (the generated frame entering VGG / the discriminator).
+    unroll = (kw, pad_left, cpad) selects the W-unrolled layout."""
+    xp = ops.image_prep(x, prep) if unroll is None else ops.image_prep_unrolled(x, unroll[0], unroll[1], unroll[2], prep)
     if ctx.tape is not None:
         tape = ctx.tape
 
@@ -272,7 +282,10 @@ def _prep_with_grad(ctx, x, prep):
             if g is None:
                 return
             dx, acc = tape.acquire(x)
-            ops.image_prep_bwd(g, dx, prep, accumulate=acc)
+            if unroll is None:
+                ops.image_prep_bwd(g, dx, prep, accumulate=acc)
+            else:
+                ops.image_prep_unrolled_bwd(g, dx, unroll[0], unroll[1], prep, accumulate=acc)
         tape.record(bwd)
     return xp
 

@@ -35,8 +35,16 @@ def load_npy_into(ctx, vgg19_path):
     return ctx.load_state_dict(sd)
 
 
+VGG_UNROLL = (3, 1, 16)   # conv1_1 as a 3x1 convolution over 3 horizontal taps x 3 channels (9 of 16 channels used)
+
+
+def prepare(x, prep):
+    """float32 image -> W-unrolled bf16 VGG input (ops.image_prep_unrolled with `prep` = affine map + channel order)."""
+    return ops.image_prep_unrolled(x.contiguous(), VGG_UNROLL[0], VGG_UNROLL[1], VGG_UNROLL[2], prep)
+
+
 def features_from_prepared(xp, need_input_grad):
-    """xp: bf16 [N,H,W,16] already in VGG input space (BGR minus mean, channels 3..15 zero)."""
+    """xp: W-unrolled bf16 [N,H,W,16] in VGG input space (BGR minus mean), see prepare()."""
     from . import maxpool
     ctx = _ctx()
     feats = []
@@ -46,8 +54,9 @@ def features_from_prepared(xp, need_input_grad):
         if name == "pool":
             x = maxpool(x)
             continue
-        x = E.conv_layer(ctx, [x], "vgg/%s/filter" % name, "vgg/%s/biases" % name, 3, 1, 0, act=tc.ACT_RELU,
-                         need_input_grad=(need_input_grad or not first))
+        x = E.conv_layer(ctx, [x], "vgg/%s/filter" % name, "vgg/%s/biases" % name, (3, 1) if first else 3, 1, 0,
+                         act=tc.ACT_RELU, need_input_grad=(need_input_grad or not first),
+                         wshape=(3, 1, 9, 64) if first else None)
         first = False
         if name in _TAPS:
             feats.append(x)
@@ -63,4 +72,4 @@ class Vgg19:
     def build(self, rgb):
         """rgb: float32 NHWC in [0,255] (reference vgg.py:13-43) -> the five feature maps."""
         prep = ((1.0, 1.0, 1.0), tuple(-m for m in ops.VGG_MEAN), (2, 1, 0))
-        return features_from_prepared(ops.image_prep(rgb.contiguous(), prep), need_input_grad=False)
+        return features_from_prepared(prepare(rgb, prep), need_input_grad=False)

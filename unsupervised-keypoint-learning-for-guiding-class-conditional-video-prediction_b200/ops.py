@@ -47,6 +47,27 @@ def image_prep_bwd(g, dx, prep=IDENT_PREP, accumulate=False):
     return dx
 
 
+def image_prep_unrolled(x, kw, pad_left, cpad, prep=IDENT_PREP):
+    """f32 [N,H,W,3] -> bf16 [N,H,W,cpad] with out[..., j*3+c] = prep(x[..., w+j-pad_left, c]) (zero outside): turns a
+    KHxKW first-layer convolution into a KHx1 one over KW*3 channels."""
+    assert x.dtype == F32 and x.dim() == 4 and x.shape[-1] == 3 and x.is_cuda
+    x = x.contiguous()
+    N, H, W, _ = x.shape
+    out = torch.empty((N, H, W, cpad), device=x.device, dtype=BF16)
+    a, b, perm = prep
+    _lib.call("kp_image_prep_unrolled", _p(x), N, H, W, int(kw), int(pad_left), int(cpad), _f3(a), _f3(b), _i3(perm), _p(out),
+              _st())
+    return out
+
+
+def image_prep_unrolled_bwd(g, dx, kw, pad_left, prep=IDENT_PREP, accumulate=False):
+    a, _, perm = prep
+    N, H, W, cpad = g.shape
+    _lib.call("kp_image_prep_unrolled_bwd", _p(g), N, H, W, int(kw), int(pad_left), int(cpad), _f3(a), _i3(perm),
+              1 if accumulate else 0, _p(dx), _st())
+    return dx
+
+
 def bn_finalize(ssum, ssq, bias, gamma, beta, count, moving_mean, moving_var, eps=1e-5, decay=0.999):
     C = gamma.shape[0]
     dev = gamma.device
@@ -67,13 +88,20 @@ def bn_act_apply(x, scale, shift, relu=True, upsample=False):
     return out
 
 
-def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False):
+def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False, gbeta_acc=None, ggamma_acc=None,
+               zeroed=None):
+    """`zeroed`: optional pre-zeroed f32 buffer of >= 2*C elements for this call's dbeta/dgamma sums (saves two
+    memsets); gbeta_acc / ggamma_acc: parameter-gradient views that receive += dbeta / dgamma inside the kernel."""
     N, H, W, C = x.shape
-    dbeta = torch.empty(C, device=x.device, dtype=F32)
-    dgamma = torch.empty(C, device=x.device, dtype=F32)
+    if zeroed is not None:
+        dbeta, dgamma, pre = zeroed[:C], zeroed[C:2 * C], 1
+    else:
+        dbeta = torch.empty(C, device=x.device, dtype=F32)
+        dgamma = torch.empty(C, device=x.device, dtype=F32)
+        pre = 0
     dx = torch.empty_like(x)
     _lib.call("kp_bn_act_bwd", _p(dout), _p(x), _p(scale), _p(shift), _p(mean), _p(rstd), 1 if relu else 0,
-              1 if upsample else 0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _st())
+              1 if upsample else 0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _p(gbeta_acc), _p(ggamma_acc), pre, _st())
     return dx, dgamma, dbeta
 
 

@@ -47,6 +47,11 @@ def round_up(v, m):
     return -(-v // m) * m
 
 
+def _khw(k):
+    """Kernel size as (kh, kw); an int means a square kernel."""
+    return (int(k[0]), int(k[1])) if isinstance(k, (tuple, list)) else (int(k), int(k))
+
+
 def pick_cb(channels):
     for cb in (64, 32):
         if all(c % cb == 0 for c in channels):
@@ -143,10 +148,11 @@ def plan_conv_fwd(src_shapes, k, stride, pad, cout, out_channels_total=None, out
         assert s[:3] == (N, H, W), "concat sources must share N,H,W"
     Cs = [s[3] for s in src_shapes]
     cin = sum(Cs)
+    k_h, k_w = _khw(k)
     Hp, Wp = H + 2 * pad, W + 2 * pad
     Ho, Wo = -(-Hp // stride), -(-Wp // stride)
-    pt = pad + same_pad(Hp, k, stride)[0]
-    pl = pad + same_pad(Wp, k, stride)[0]
+    pt = pad + same_pad(Hp, k_h, stride)[0]
+    pl = pad + same_pad(Wp, k_w, stride)[0]
     p = TapPlan()
     p.N = N
     p.CB = pick_cb(Cs)
@@ -155,16 +161,16 @@ def plan_conv_fwd(src_shapes, k, stride, pad, cout, out_channels_total=None, out
     if stride == 1:
         for i, C in enumerate(Cs):
             p.views.append(dict(src=i, C=C, Wd=W, Hd=H, off=0, sw=C, sh=W * C, sn=H * W * C))
-        for kh in range(k):
-            for kw in range(k):
+        for kh in range(k_h):
+            for kw in range(k_w):
                 p.taps.append((kh - pt, kw - pl, 0))
                 tap_k.append((kh, kw))
     elif stride == 2:
         assert len(Cs) == 1, "stride-2 convolutions take a single source on this path"
         C = Cs[0]
         used = {}
-        for kh in range(k):
-            for kw in range(k):
+        for kh in range(k_h):
+            for kw in range(k_w):
                 eh, ew = kh - pt, kw - pl
                 ph, pw = eh % 2, ew % 2
                 key = (ph, pw)
@@ -185,7 +191,7 @@ def plan_conv_fwd(src_shapes, k, stride, pad, cout, out_channels_total=None, out
     for C in Cs:
         segs.append((base, C))
         base += C
-    _finish(p, cout, "fwd", [kh * k + kw for kh, kw in tap_k], segs)
+    _finish(p, cout, "fwd", [kh * k_w + kw for kh, kw in tap_k], segs)
     return p, (N, Ho, Wo)
 
 
@@ -199,10 +205,11 @@ def plan_conv_dgrad(x_shape, k, stride, pad, cout, cin_slice=None):
     N, H, W, Cx = x_shape
     c0, c1, cin_total = (0, Cx, Cx) if cin_slice is None else cin_slice
     assert c1 - c0 == Cx
+    k_h, k_w = _khw(k)
     Hp, Wp = H + 2 * pad, W + 2 * pad
     Ho, Wo = -(-Hp // stride), -(-Wp // stride)
-    pt = pad + same_pad(Hp, k, stride)[0]
-    pl = pad + same_pad(Wp, k, stride)[0]
+    pt = pad + same_pad(Hp, k_h, stride)[0]
+    pl = pad + same_pad(Wp, k_w, stride)[0]
     plans = []
     classes = [(0, 0)] if stride == 1 else [(0, 0), (0, 1), (1, 0), (1, 1)]
     for ah, aw in classes:
@@ -212,8 +219,8 @@ def plan_conv_dgrad(x_shape, k, stride, pad, cout, cin_slice=None):
         p.n_src = 1
         p.views.append(dict(src=0, C=cout, Wd=Wo, Hd=Ho, off=0, sw=cout, sh=Wo * cout, sn=Ho * Wo * cout))
         tap_k = []
-        for kh in range(k):
-            for kw in range(k):
+        for kh in range(k_h):
+            for kw in range(k_w):
                 if stride == 1:
                     p.taps.append((pt - kh, pl - kw, 0))
                     tap_k.append((kh, kw))
@@ -233,7 +240,7 @@ def plan_conv_dgrad(x_shape, k, stride, pad, cout, cin_slice=None):
                 continue
             p.out_off, p.out_sw, p.out_sh, p.out_sn = (ah * W + aw) * Cx, 2 * Cx, 2 * W * Cx, H * W * Cx
 
-        _finish(p, Cx, "dgrad", [kh * k + kw for kh, kw in tap_k], [(0, cout)], row_slice=(c0, c1))
+        _finish(p, Cx, "dgrad", [kh * k_w + kw for kh, kw in tap_k], [(0, cout)], row_slice=(c0, c1))
         plans.append(p)
     return plans
 
