@@ -33,6 +33,7 @@ struct alignas(64) TapConvKParams {
     int TW, TH, TN, tiles_w, tiles_h;
     int Ho, Wo, N;
     int BN, n_tiles, total_tiles, tmem_cols, stages, total_iters;
+    int ksplit, groups_per_split, bpt;      // split-K over CTAs (fp32 atomic epilogue), blocks per tap
     uint32_t a_bytes, b_bytes, stage_bytes;
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
@@ -140,14 +141,19 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 if (p.nblk[m] > 0) tma_prefetch_desc(&p.mapA[m]);
             tma_prefetch_desc(&p.mapB);
             uint32_t git = 0;   // ring position (one per GROUP of G channel blocks), keeps counting across tiles
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x) {
+                const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
                 const int n_off = nt * p.BN;
-                int t = 0, s = 0, cb = 0;       // (tap, source, channel block) of the next K block
-                for (int it0 = 0; it0 < p.total_iters; it0 += G, ++git) {
-                    const int nv = min(G, p.total_iters - it0);
+                const int it_begin = ks * p.groups_per_split * G;
+                const int it_end = min(p.total_iters, (ks + 1) * p.groups_per_split * G);
+                // (tap, source, channel block) of the first K block of this split
+                int t = it_begin / p.bpt, s = 0, cb = it_begin - t * p.bpt;
+                while (cb >= p.nblk[p.mf[t] + s]) { cb -= p.nblk[p.mf[t] + s]; ++s; }
+                for (int it0 = it_begin; it0 < it_end; it0 += G, ++git) {
+                    const int nv = min(G, it_end - it0);
                     const uint32_t st = git % (uint32_t)S;
                     if (git >= (uint32_t)S) mbar_wait(&empty[st], ((git / (uint32_t)S) - 1) & 1);
                     uint8_t* a_dst = base + (size_t)st * p.stage_bytes;
@@ -170,13 +176,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
             const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
             uint32_t git = 0;
             int lt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+            for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++lt) {
+                const int ks = work % p.ksplit;
+                const int it_begin = ks * p.groups_per_split * G;
+                const int it_end = min(p.total_iters, (ks + 1) * p.groups_per_split * G);
                 const int acc = lt & 1;
                 if (lt >= 2) mbar_wait(&tempty[acc], ((lt >> 1) - 1) & 1);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * p.BN);
-                for (int it0 = 0; it0 < p.total_iters; it0 += G, ++git) {
-                    const int nv = min(G, p.total_iters - it0);
+                for (int it0 = it_begin; it0 < it_end; it0 += G, ++git) {
+                    const int nv = min(G, it_end - it0);
                     const uint32_t st = git % (uint32_t)S;
                     mbar_wait(&full[st], (git / (uint32_t)S) & 1);
                     tc_fence_after();
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                             // the 16-element slice of block g / step k sits (g*CB + k*16)*2 bytes into the row
                             const uint64_t da = umma_smem_desc(a_addr + g * A_BOX_BYTES + k * 32, SBO, 16, LAYOUT);
                             const uint64_t db = umma_smem_desc(b_addr + (g * CB + k * 16) * 2, 1024, 16, 2u);
-                            umma_bf16(d_tmem, da, db, idesc, (it0 | g | k) != 0 ? 1u : 0u);
+                            umma_bf16(d_tmem, da, db, idesc, ((it0 - it_begin) | g | k) != 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty[st]);
@@ -203,7 +212,8 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         const int row = q * 32 + lane;
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
         int lt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++lt) {
+            const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
             const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -242,7 +252,17 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 // activation is selected by ONE warp-uniform branch per chunk (the first version indexed v[]
                 // dynamically -> local memory, and evaluated the activation switch per element: ~8000 instructions
                 // per warp per tile, which made the whole kernel epilogue-bound).
-                if (valid && ch0 < p.Cout) {
+                if (p.ksplit > 1) {
+                    // split-K partial tile: fp32 atomic accumulation into the zeroed output (host guarantees f32 output,
+                    // no activation); the bias is contributed once, by split 0
+                    if (valid && ch0 < p.Cout) {
+                        float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
+                        const int nvalid = p.Cout - ch0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nvalid) atomicAdd(o + j, v[j] + ((ks == 0 && p.bias != nullptr) ? __ldg(p.bias + ch0 + j) : 0.f));
+                    }
+                } else if (valid && ch0 < p.Cout) {
                     if (p.bias != nullptr) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch0);   // [Cout_pad], 64-byte aligned chunk
 #pragma unroll
@@ -489,6 +509,27 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.total_tiles = p.tiles_w * p.tiles_h * tiles_n * p.n_tiles;
     p.tmem_cols = pow2_at_least(2 * BN, 32);          // double-buffered accumulator
     p.total_iters = total_iters;
+    p.bpt = total_blocks_per_tap;
+    p.ksplit = 1;
+    {
+        // split-K for long-K launches with very few tiles (img_discr D_logit: 18 tiles x 288 K-groups): fp32 output,
+        // no activation, contiguous output so that it can be zeroed here
+        const int G = 64 / CB;
+        const int n_groups = (total_iters + G - 1) / G;
+        const bool contiguous = d->out_off == 0 && d->out_sw == d->Cout && d->out_sh == (long long)d->Wo * d->Cout &&
+                                d->out_sn == (long long)d->Ho * d->Wo * d->Cout;
+        if (d->out_f32 && d->act == KP_ACT_NONE && !d->accumulate && ssum == nullptr && contiguous && n_groups >= 32 &&
+            p.total_tiles * 2 <= device_sm_count()) {
+            int ks = device_sm_count() / p.total_tiles;
+            if (ks > n_groups / 8) ks = n_groups / 8;
+            if (ks > 1) {
+                p.groups_per_split = (n_groups + ks - 1) / ks;
+                p.ksplit = (n_groups + p.groups_per_split - 1) / p.groups_per_split;
+                KP_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)d->N * d->Ho * d->Wo * d->Cout * sizeof(float), st));
+            }
+        }
+        if (p.ksplit == 1) p.groups_per_split = n_groups;
+    }
     p.a_bytes = 128u * 64u * 2u;                       // G = 64/CB activation boxes of 128 x CB
     p.b_bytes = (uint32_t)BN * 64u * 2u;               // one weight box [BN][64]
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
@@ -509,7 +550,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
 
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
     int grid = device_sm_count() * ctas_per_sm;
-    if (grid > p.total_tiles) grid = p.total_tiles;
+    if (grid > p.total_tiles * p.ksplit) grid = p.total_tiles * p.ksplit;
 #define KP_LAUNCH_TAPCONV(CBV)                                                                                      \
     do {                                                                                                            \
         static bool attr_done = false;                                                                              \

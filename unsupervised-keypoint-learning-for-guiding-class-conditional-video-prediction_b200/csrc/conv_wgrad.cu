@@ -208,7 +208,8 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     // taps per CTA: limited by TMEM (T accumulators of BN columns) and by shared memory (<= 11 boxes = 88 KB per stage)
     int t_max = 512 / p.BN;
     const size_t slack = (size_t)(128 / CB - p.n_a_max) * p.box_bytes;
-    const int boxes_per_stage = (int)(((215u * 1024u - slack) / 2) / p.box_bytes);   // two stages must fit
+    int boxes_per_stage = (int)(((215u * 1024u - slack) / 2) / p.box_bytes);   // two stages must fit ...
+    if (boxes_per_stage > 8) boxes_per_stage = 8;   // ... but 3-4 stages hide the TMA latency much better (<= 64 KB per stage)
     const int by_smem = (boxes_per_stage - p.n_b_max) / p.n_a_max;
     if (t_max > by_smem) t_max = by_smem;
     if (t_max > d->n_taps) t_max = d->n_taps;
