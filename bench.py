@@ -172,7 +172,7 @@ class CpuTrainer:
         with torch.no_grad():
             for name, val in ctx.updates:
                 self.P[name] = val.detach()
-        return float(lD), float(lG)
+        return float(lD.detach()), float(lG.detach())
 
 
 def cpu_train(batch, steps, warmup=1):
@@ -225,6 +225,9 @@ def _dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout: send it to a file so that stdout
+        # stays ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/kp_b200_nccl.%h.%p.log")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         torch.cuda.set_device(local_rank)
@@ -305,7 +308,10 @@ def run_ours(args):
                               "unit": "frames/s", "n_gpus": world, "steps": r["steps"], "warmup": args.warmup,
                               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                               "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"]},
-                              "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]}))
+                              "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]}), flush=True)
+        if world > 1:
+            torch.distributed.barrier()
+            os._exit(0)
         return
 
     # ------------------------------ train workload ------------------------------
@@ -439,10 +445,16 @@ def run_ours(args):
         }
         if k1r is not None:
             line["k1"] = k1r
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down in a safe order: drop the captured graph (it holds NCCL kernels) before the communicator goes,
+        # and leave through os._exit so that no destructor can block on a peer that is already gone.
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        model._graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
