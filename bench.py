@@ -330,9 +330,8 @@ def run_ours(args):
     model.build(feed)
     launches_per_step = None
     if not args.no_graph:
-        n0 = lib.kp_launch_count()
         model.enable_cuda_graph(B)
-        launches_per_step = int(lib.kp_launch_count() - n0) // 2       # warm-up step + captured step
+        launches_per_step = model.graph_launches                         # library kernels recorded in the captured step
     for _ in range(args.warmup):
         model.train_step()
     _barrier(world)
@@ -392,13 +391,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         model._graph = saved
         if os.environ.get("KP_BENCH_CONV_DETAIL"):
-            rows = sorted(((e0.elapsed_time(e1), kind, f) for kind, f, e0, e1 in cv.PROFILE), reverse=True)
-            for ms_, kind, f in rows[:40]:
-                sys.stderr.write("conv %-6s %8.1f us %8.1f GFLOP %7.1f TFLOP/s\n" % (kind, ms_ * 1e3, f / 1e9, f / (ms_ * 1e-3) / 1e12))
-        tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in cv.PROFILE)
-        tot_fl = sum(f for _, f, _, _ in cv.PROFILE)
+            rows = sorted(((e0.elapsed_time(e1), kind, f, tag) for kind, f, e0, e1, tag in cv.PROFILE), reverse=True)
+            for ms_, kind, f, tag in rows[:int(os.environ.get("KP_BENCH_CONV_DETAIL_ROWS", "60"))]:
+                sys.stderr.write("conv %-6s %8.1f us %8.1f GFLOP %7.1f TFLOP/s  %s\n" % (kind, ms_ * 1e3, f / 1e9, f / (ms_ * 1e-3) / 1e12, tag))
+        tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in cv.PROFILE)
+        tot_fl = sum(f for _, f, _, _, _ in cv.PROFILE)
         by = {}
-        for kind, f, e0, e1 in cv.PROFILE:
+        for kind, f, e0, e1, _ in cv.PROFILE:
             a = by.setdefault(kind, [0.0, 0.0, 0])
             a[0] += f; a[1] += e0.elapsed_time(e1); a[2] += 1
         kern = {"conv_launches": len(cv.PROFILE), "conv_ms": tot_ms, "conv_tflops": tot_fl / (tot_ms * 1e-3) / 1e12,

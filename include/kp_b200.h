@@ -174,6 +174,17 @@ typedef struct {
     int Kper, rows_pad, Ktot;
 } kp_pack_desc;
 int kp_pack_weights(const float* w, const kp_pack_desc* desc, const float* row_scale, void* dst, void* stream);
+/* The same re-layout for MANY kernels in one launch (all convolutions of one optimiser are re-packed right after its
+ * Adam step).  `jobs_dev` is a DEVICE array of n_jobs kp_pack_job (built once by the host, block_begin = exclusive
+ * prefix sum of kp_pack_job_blocks() over the jobs, total_blocks = the sum).                                  */
+typedef struct {
+    const float* w;                        /* device: fp32 HWIO kernel */
+    void* dst;                             /* device: bf16 [rows_pad][Ktot] */
+    kp_pack_desc d;
+    int block_begin, n_blocks;
+} kp_pack_job;
+int kp_pack_job_blocks(const kp_pack_desc* desc);
+int kp_pack_weights_batch(const void* jobs_dev, int n_jobs, int total_blocks, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Memory-bound companions (bf16 NHWC, 8-channel vectors; fp32 only at the reference boundary)
@@ -207,6 +218,13 @@ int kp_bn_finalize(const float* stats_sum, const float* stats_sq, const float* c
  * bilinear, models/networks/__init__.py:63,98): x bf16 [N,H,W,C] -> out bf16 [N,H,W,C] or [N,2H,2W,C].  */
 int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W,
                     int C, void* out, void* stream);
+/* kp_bn_finalize + kp_bn_act_apply in ONE launch (the training-mode path of layers.batch_norm followed by tf.nn.relu,
+ * models/networks/__init__.py:11-12 etc.): every block derives scale/shift from the raw sums, block 0 publishes
+ * scale/shift/save_mean/save_rstd and updates the moving averages.  Same argument meaning as the two calls.  */
+int kp_bn_stats_apply(const float* stats_sum, const float* stats_sq, const float* conv_bias, const float* gamma,
+                      const float* beta, double count, float eps, float decay, float* moving_mean, float* moving_var,
+                      float* scale, float* shift, float* save_mean, float* save_rstd, const void* x, int relu, int upsample,
+                      int N, int H, int W, int C, void* out, void* stream);
 /* backward of kp_bn_act_apply + batch-norm statistics: dout (grad of the output, upsampled size if upsample),
  * x (the conv output saved by the forward) -> dbeta, dgamma f32 [C] (this call's sums; zeroed by the library
  * unless prezeroed != 0) and dx bf16 [N,H,W,C].  gbeta_acc / ggamma_acc (nullable): parameter-gradient buffers

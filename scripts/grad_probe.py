@@ -92,6 +92,9 @@ PERF = {
     "det_128_32": (32, 128, 128, [32], 3, 1, 32),
     "det_128_16": (32, 128, 128, [16], 3, 1, 16),
     "enc_s2_64": (32, 128, 128, [32], 3, 2, 64),
+    "head_128_16_40": (32, 128, 128, [16], 1, 1, 40),
+    "det_128_48_16": (32, 128, 128, [16, 32], 3, 1, 16),
+    "vggfirst_128_16_64": (64, 128, 128, [16], 3, 1, 64),
 }
 
 
@@ -113,7 +116,7 @@ def run_perf():
         out = torch.empty((n, ho, wo, cout), device=dev, dtype=torch.bfloat16)
         bias = torch.zeros(plan.rows_pad, device=dev)
         dy = torch.randn((n, ho, wo, cout), device=dev).to(torch.bfloat16)
-        wplan = tc.plan_conv_wgrad(tuple(xs[0].shape), k, s, 0, cout)
+        wplan = tc.plan_conv_wgrad(tuple(xs[0].shape), k, s, 0, cout, cin_slice=(0, Cs[0], cin) if len(Cs) > 1 else None)
         dw = torch.zeros((k, k, cin, cout), device=dev)
 
         def timeit(fn, reps=reps_env):
@@ -129,11 +132,19 @@ def run_perf():
             return e0.elapsed_time(e1) / reps
 
         t_f = timeit(lambda: conv.run_plan(plan, xs, wp, bias, out, act=tc.ACT_RELU))
+        extra = {}
+        if os.environ.get("PERF_VARIANTS"):
+            ssum = torch.zeros(plan.rows_pad, device=dev)
+            ssq = torch.zeros(plan.rows_pad, device=dev)
+            out32 = torch.empty((n, ho, wo, cout), device=dev, dtype=torch.float32)
+            extra["fwd_stats_ms"] = timeit(lambda: conv.run_plan(plan, xs, wp, None, out, stats=(ssum, ssq)))
+            extra["fwd_nobias_noact_ms"] = timeit(lambda: conv.run_plan(plan, xs, wp, None, out))
+            extra["fwd_f32_ms"] = timeit(lambda: conv.run_plan(plan, xs, wp, bias, out32))
         t_w = timeit(lambda: conv.run_wgrad(wplan, xs[0], dy, dw))
         flop = 2.0 * n * ho * wo * k * k * cin * cout
         byt = 2.0 * (sum(x.numel() for x in xs) + out.numel())
         print(json.dumps({"perf": name, "fwd_ms": t_f, "fwd_tflops": flop / t_f / 1e9, "fwd_gbs_min": byt / t_f / 1e6,
-                          "wgrad_ms": t_w, "wgrad_tflops": flop / t_w / 1e9}), flush=True)
+                          "wgrad_ms": t_w, "wgrad_tflops": flop / t_w / 1e9, **extra}), flush=True)
 
 
 if __name__ == "__main__":

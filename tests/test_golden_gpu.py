@@ -63,7 +63,7 @@ def test_stage1_model_matches_reference_fixture(cuda_dev, training):
     im, fut = [torch.from_numpy(a.astype(np.float32)).to(cuda_dev) for a in S["stage1_inputs"]()]
     model = models.DetectorTranslatorModel(CFG, is_training=True, device=cuda_dev)
     model.ctx.load_state_dict(P)
-    model.global_step.value.fill_(12345)
+    model.global_step.value = 12345
     model.build({"image": im, "future_image": fut})
     model.is_training = training
     lD, lG, _, _ = model.test_step()             # BN mode follows is_training; no parameter update

@@ -37,6 +37,8 @@ SIGNATURES = {
     "kp_image_prep_bwd": [c_vp, c_ll, c_vp, c_vp, c_int, c_vp, c_vp],
     "kp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_double, c_float, c_float, c_vp, c_vp, c_vp, c_vp,
                        c_vp, c_vp, c_vp],
+    "kp_bn_stats_apply": [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_float, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                          c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_apply": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                       c_vp, c_vp, c_int, c_vp],
@@ -52,6 +54,8 @@ SIGNATURES = {
     "kp_adam_tf": [c_vp, c_vp, c_vp, c_vp, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, c_vp, c_vp],
     "kp_channel_sum": [c_vp, c_ll, c_int, c_vp, c_vp],
     "kp_pack_weights": [c_vp, c_vp, c_vp, c_vp, c_vp],
+    "kp_pack_job_blocks": [c_vp],
+    "kp_pack_weights_batch": [c_vp, c_int, c_int, c_vp],
     "kp_image_prep_unrolled": [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "kp_image_prep_unrolled_bwd": [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
 }

@@ -22,8 +22,8 @@ PROFILE = None
 
 
 class _Timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, tag=""):
+        self.kind, self.flops, self.tag = kind, flops, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -34,7 +34,7 @@ class _Timed:
     def __exit__(self, *a):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1, self.tag))
 
 
 def pack_weights(plan, w, row_scale=None):
@@ -55,6 +55,34 @@ def pack_weights(plan, w, row_scale=None):
         _lib.call("kp_pack_weights", w.data_ptr(), ctypes.byref(d), None if rs is None else rs.data_ptr(), out.data_ptr(),
                   _stream())
     return out
+
+
+class PackTable:
+    """Device job table for kp_pack_weights_batch: re-packs many (plan, fp32 HWIO kernel view, packed bf16 output)
+    triples with ONE launch.  The table is uploaded once per job list (never inside a CUDA-graph capture)."""
+
+    def __init__(self, jobs, device):
+        lib = _lib.load()
+        arr = (tc.PackJob * len(jobs))()
+        total = 0
+        for i, (plan, w, out) in enumerate(jobs):
+            if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+                raise ValueError("PackTable: kernels must be contiguous float32 CUDA tensors")
+            d = tc.pack_desc(plan, tuple(w.shape))
+            nb = lib.kp_pack_job_blocks(ctypes.byref(d))
+            if nb <= 0:
+                raise ValueError("PackTable: bad pack descriptor for job %d" % i)
+            arr[i].w, arr[i].dst, arr[i].d = w.data_ptr(), out.data_ptr(), d
+            arr[i].block_begin, arr[i].n_blocks = total, nb
+            total += nb
+        self.n_jobs, self.total_blocks = len(jobs), total
+        self.keep = [(w, out) for _, w, out in jobs]          # the table holds raw pointers
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = host.to(device)
+
+    def run(self):
+        with torch.cuda.device(self.table.device):
+            _lib.call("kp_pack_weights_batch", self.table.data_ptr(), self.n_jobs, self.total_blocks, _stream())
 
 
 def pack_weights_torch(plan, w, row_scale=None, dtype=torch.bfloat16):
@@ -127,7 +155,9 @@ def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None
     first = plan.taps[0][2]
     k_real = len(plan.taps) * sum(plan.views[first + s]["C"] for s in range(plan.n_src))
     flops = 2.0 * plan.N * plan.Ho * plan.Wo * k_real * plan.rows * getattr(plan, "flop_scale", 1.0)
-    with torch.cuda.device(out.device), _Timed("dgrad" if plan.pack["mode"] == "dgrad" else "fwd", flops):
+    tag = "N%d %dx%d K%d(taps %d) -> %d CB%d%s" % (plan.N, plan.Ho, plan.Wo, plan.Ktot, len(plan.taps), plan.rows, plan.CB,
+                                                  " +stats" if stats is not None else "") if PROFILE is not None else ""
+    with torch.cuda.device(out.device), _Timed("dgrad" if plan.pack["mode"] == "dgrad" else "fwd", flops, tag):
         _lib.call("kp_tapconv_bf16", ctypes.byref(d), ptrs, wpacked.data_ptr(),
                   None if bias is None else bias.data_ptr(), out.data_ptr(),
                   None if ssum is None else ssum.data_ptr(), None if ssq is None else ssq.data_ptr(), _stream())
@@ -143,6 +173,7 @@ def run_wgrad(plan, x, dy, dw, splits=0):
         raise ValueError("dW must be a contiguous f32 CUDA tensor (HWIO)")
     d = plan.desc(splits)
     flops = 2.0 * plan.N * plan.Ho * plan.Wo * len(plan.taps) * plan.Cin * plan.Cout * getattr(plan, "flop_scale", 1.0)
-    with torch.cuda.device(dw.device), _Timed("wgrad", flops):
+    tag = "N%d %dx%d Cin%d Cout%d taps %d CB%d" % (plan.N, plan.Ho, plan.Wo, plan.Cin, plan.Cout, len(plan.taps), plan.CB)
+    with torch.cuda.device(dw.device), _Timed("wgrad", flops, tag):
         _lib.call("kp_tapconv_wgrad_bf16", ctypes.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream())
     return dw

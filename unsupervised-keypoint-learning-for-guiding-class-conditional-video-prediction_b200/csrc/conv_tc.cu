@@ -37,7 +37,7 @@ struct alignas(64) TapConvKParams {
     uint32_t a_bytes, b_bytes, stage_bytes;
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
-    int Cout, out_f32, act, accumulate;
+    int Cout, cout_pad, out_f32, act, accumulate;
     float alpha;
     const float* bias;
     float* ssum;
@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
     uint64_t* tfull = empty + p.stages;   // [2] accumulator buffer ready for the epilogue
     uint64_t* tempty = tfull + 2;         // [2] accumulator buffer drained
     uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
+    // per-CTA copies for the epilogue: bias [Cout_pad] and the batch-norm partial sums [2][Cout_pad]
+    float* s_bias = reinterpret_cast<float*>(tslot + 4);
+    float* s_stat = s_bias + p.cout_pad;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -211,6 +214,15 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+        // Stage the bias in shared memory once (a global load per 16-column chunk was the top stall of the epilogue
+        // on the short-K layers) and keep the batch-norm partial sums per CTA: they are flushed with ONE global atomic
+        // per channel per CTA after the last tile instead of one per channel per warp per tile.
+        const int et = threadIdx.x - 64;
+        if (p.bias != nullptr)
+            for (int i = et; i < p.cout_pad; i += 128) s_bias[i] = __ldg(p.bias + i);
+        if (p.ssum != nullptr)
+            for (int i = et; i < 2 * p.cout_pad; i += 128) s_stat[i] = 0.f;
+        named_bar_sync(1, 128);
         int lt = 0;
         for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++lt) {
             const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
@@ -244,8 +256,8 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                     const float s2 = warp_colsum16(sq, lane);
                     if ((lane & 1) == 0) {
                         const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(p.ssum + ch0 + col, s1);
-                        atomicAdd(p.ssq + ch0 + col, s2);
+                        atomicAdd(s_stat + ch0 + col, s1);
+                        atomicAdd(s_stat + p.cout_pad + ch0 + col, s2);
                     }
                 }
                 // Everything below is fully unrolled with compile-time indices so v[] stays in registers, and the
@@ -260,14 +272,14 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                         const int nvalid = p.Cout - ch0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (j < nvalid) atomicAdd(o + j, v[j] + ((ks == 0 && p.bias != nullptr) ? __ldg(p.bias + ch0 + j) : 0.f));
+                            if (j < nvalid) atomicAdd(o + j, v[j] + ((ks == 0 && p.bias != nullptr) ? s_bias[ch0 + j] : 0.f));
                     }
                 } else if (valid && ch0 < p.Cout) {
                     if (p.bias != nullptr) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch0);   // [Cout_pad], 64-byte aligned chunk
+                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + ch0);   // 64-byte aligned chunk, broadcast
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float4 b = __ldg(b4 + j);
+                            const float4 b = b4[j];
                             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                         }
                     }
@@ -288,54 +300,66 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                             if (j == last) v[j] = 1.f / (1.f + __expf(-v[j]));
                     }
                     const int nvalid = p.Cout - ch0;   // >= 1; the chunk is complete when >= 16
+                    // Vector stores per group of 4 floats / 8 bf16 wherever the group is complete (Cout = 40 leaves a
+                    // half chunk: scalar 2-byte stores at a 80-byte lane stride throttled the LSU), scalars for the rest.
                     if (p.out_f32) {
                         float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
-                        if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-                            float4* o4 = reinterpret_cast<float4*>(o);
-                            if (p.accumulate) {
+                        const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 b = o4[j];
+                        for (int j = 0; j < 4; ++j) {
+                            if (al && 4 * j + 4 <= nvalid) {
+                                float4* o4 = reinterpret_cast<float4*>(o) + j;
+                                if (p.accumulate) {
+                                    const float4 b = *o4;
                                     v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                                 }
+                                *o4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (4 * j + e < nvalid) o[4 * j + e] = p.accumulate ? o[4 * j + e] + v[4 * j + e] : v[4 * j + e];
                             }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (j < nvalid) o[j] = p.accumulate ? o[j] + v[j] : v[j];
                         }
                     } else {
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + ch0;
-                        if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-                            uint4* o4 = reinterpret_cast<uint4*>(o);
-                            if (p.accumulate) {
-                                const uint4 u0 = o4[0], u1 = o4[1];
-                                const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&u0);
-                                const __nv_bfloat162* h1p = reinterpret_cast<const __nv_bfloat162*>(&u1);
+                        const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (al && 8 * h + 8 <= nvalid) {
+                                uint4* o4 = reinterpret_cast<uint4*>(o) + h;
+                                if (p.accumulate) {
+                                    const uint4 u = *o4;
+                                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 a = __bfloat1622float2(hp[j]);
+                                        v[8 * h + 2 * j] += a.x; v[8 * h + 2 * j + 1] += a.y;
+                                    }
+                                }
+                                uint32_t w[4];
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const float2 a = __bfloat1622float2(h0p[j]), b = __bfloat1622float2(h1p[j]);
-                                    v[2 * j] += a.x; v[2 * j + 1] += a.y; v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+                                    w[j] = *reinterpret_cast<uint32_t*>(&h2);
                                 }
-                            }
-                            uint32_t w[8];
+                                *o4 = make_uint4(w[0], w[1], w[2], w[3]);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                                for (int e = 0; e < 8; ++e)
+                                    if (8 * h + e < nvalid)
+                                        o[8 * h + e] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[8 * h + e]) + v[8 * h + e]
+                                                                                        : v[8 * h + e]);
                             }
-                            o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (j < nvalid)
-                                    o[j] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[j]) + v[j] : v[j]);
                         }
                     }
                 }
+            }
+        }
+        if (p.ssum != nullptr) {
+            named_bar_sync(1, 128);
+            for (int i = et; i < p.cout_pad; i += 128) {
+                atomicAdd(p.ssum + i, s_stat[i]);
+                atomicAdd(p.ssq + i, s_stat[p.cout_pad + i]);
             }
         }
     }
@@ -535,9 +559,16 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
     // CTAs per SM: two independent pipelines per SM hide the barrier round trips of the single-thread TMA / MMA
     // issuers; the 256-wide tiles need all 512 TMEM columns and most of the shared memory, so they run alone.
+    // Short-K tiles (<= 8 K groups, narrow channel tile) are bound by the latency of the epilogue chain, not by the
+    // tensor pipe: a third CTA per SM adds epilogue warps.
+    const uint32_t epi_bytes = 3u * (uint32_t)d->Cout_pad * sizeof(float);
     int ctas_per_sm = p.tmem_cols <= 256 ? 2 : 1;
-    if (const char* e = getenv("KP_TAPCONV_CTAS_PER_SM")) ctas_per_sm = atoi(e) >= 2 && p.tmem_cols <= 256 ? 2 : 1;
-    uint32_t budget = ctas_per_sm == 2 ? 100u * 1024u : 200u * 1024u;
+    if (p.tmem_cols <= 128 && p.groups_per_split <= 8) ctas_per_sm = 3;
+    if (const char* e = getenv("KP_TAPCONV_CTAS_PER_SM")) {
+        const int want = atoi(e);
+        ctas_per_sm = want >= 3 && p.tmem_cols <= 128 ? 3 : want >= 2 && p.tmem_cols <= 256 ? 2 : 1;
+    }
+    uint32_t budget = (ctas_per_sm == 3 ? 70u : ctas_per_sm == 2 ? 108u : 216u) * 1024u - epi_bytes;
     if (const char* e = getenv("KP_TAPCONV_SMEM_KB")) budget = (uint32_t)atoi(e) * 1024u;
     int stages = (int)(budget / p.stage_bytes);
     if (stages < 2) stages = 2;
@@ -545,10 +576,10 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.stages = stages;
     p.out = out;
     p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
-    p.Cout = d->Cout; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate;
+    p.Cout = d->Cout; p.cout_pad = d->Cout_pad; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate;
     p.bias = bias; p.ssum = ssum; p.ssq = ssq;
 
-    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024 + epi_bytes;
     int grid = device_sm_count() * ctas_per_sm;
     if (grid > p.total_tiles * p.ksplit) grid = p.total_tiles * p.ksplit;
 #define KP_LAUNCH_TAPCONV(CBV)                                                                                      \

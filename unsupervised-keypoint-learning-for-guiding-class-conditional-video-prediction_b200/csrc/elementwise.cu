@@ -110,14 +110,47 @@ __global__ void bn_finalize_kernel(const float* __restrict__ ssum, const float* 
 // Per-channel scale/shift live in shared memory (two LDS.128 per 8-channel vector instead of 16 global loads).
 // Plain variant: pure streaming, two independent vectors per loop trip.  UPSAMPLE variant: one thread per INPUT
 // pixel-vector produces the 2x2 output block (4 normalised loads feed 4 stores, instead of up to 4 loads per store).
+// With fin.ssum != nullptr the kernel also does the work of bn_finalize_kernel: every block derives scale/shift from the
+// raw sums (C <= a few hundred values), block 0 publishes scale/shift/mean/rstd for the backward pass and updates the
+// moving averages - one launch per batch-norm layer instead of two.
+struct BnFin {
+    const float *ssum, *ssq, *bias, *gamma, *beta;
+    float count, eps, decay;
+    float *moving_mean, *moving_var, *scale, *shift, *save_mean, *save_rstd;
+};
 template <bool UPSAMPLE>
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                    int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out) {
+                    const BnFin fin, int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out) {
     extern __shared__ float sp[];   // [2][C]
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        sp[i] = scale ? scale[i] : 1.f;
-        sp[C + i] = scale ? shift[i] : 0.f;
+    if (fin.ssum != nullptr) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const double m0 = (double)fin.ssum[c] / fin.count;
+            double var = (double)fin.ssq[c] / fin.count - m0 * m0;
+            if (var < 0.0) var = 0.0;
+            const float mean = (float)m0 + (fin.bias ? fin.bias[c] : 0.f);
+            const float rstd = rsqrtf((float)var + fin.eps);
+            const float sc = fin.gamma[c] * rstd;
+            const float sh = fin.beta[c] - mean * sc;
+            sp[c] = sc;
+            sp[C + c] = sh;
+            if (blockIdx.x == 0) {
+                fin.scale[c] = sc;
+                fin.shift[c] = sh;
+                if (fin.save_mean) fin.save_mean[c] = mean;
+                if (fin.save_rstd) fin.save_rstd[c] = rstd;
+                if (fin.moving_mean) {
+                    const float unbiased = (float)(var * (fin.count / fmax(fin.count - 1.0, 1.0)));
+                    fin.moving_mean[c] = fin.moving_mean[c] * fin.decay + mean * (1.f - fin.decay);
+                    fin.moving_var[c] = fin.moving_var[c] * fin.decay + unbiased * (1.f - fin.decay);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            sp[i] = scale ? scale[i] : 1.f;
+            sp[C + i] = scale ? shift[i] : 0.f;
+        }
     }
     __syncthreads();
     const int CG = C >> 3;
@@ -269,27 +302,32 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
         bf8_unpack(*reinterpret_cast<const uint4*>(x + p * C + cg * 8), xv);
         accum(g, xv);
     }
-    __shared__ float red[2][256 * 8 / 1];  // [2][threads][8] would be 16 KB; reuse by striding below
-    // reduce over pixel lanes sharing a channel group
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        red[0][threadIdx.x * 8 + j] = sb[j];
-        red[1][threadIdx.x * 8 + j] = sg[j];
-    }
+    // Reduce over the pixel lanes that share a channel group: shuffles inside the warp (lanes cg, cg+CG, ...), then
+    // shared-memory atomics across the 8 warps, then ONE global atomic per channel per block.  (The first version let
+    // the CG threads of pixel lane 0 walk all other lanes serially: 2 threads x 127 lanes for C = 16.)
+    __shared__ float red[2][2048];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i / C][i % C] = 0.f;
     __syncthreads();
-    if (pl == 0) {
-        for (int l = 1; l < lanes; ++l) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sb[j] += red[0][(l * CG + cg) * 8 + j];
-                sg[j] += red[1][(l * CG + cg) * 8 + j];
-            }
-        }
+    if (CG < 32) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            atomicAdd(dbeta + cg * 8 + j, sb[j]);
-            atomicAdd(dgamma + cg * 8 + j, sg[j]);
+            for (int off = 16; off >= CG; off >>= 1) {
+                sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], off);
+                sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], off);
+            }
         }
+    }
+    if ((threadIdx.x & 31) < CG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&red[0][cg * 8 + j], sb[j]);
+            atomicAdd(&red[1][cg * 8 + j], sg[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(dbeta + c, red[0][c]);
+        atomicAdd(dgamma + c, red[1][c]);
     }
 }
 
@@ -665,18 +703,30 @@ int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const
     KP_LAUNCHED();
     return KP_OK;
 }
-int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
-                    void* out, cudaStream_t st) {
+static int bn_apply_launch(const void* x, const float* scale, const float* shift, const BnFin& fin, int relu, int upsample, int N,
+                           int H, int W, int C, void* out, cudaStream_t st) {
     KP_REQUIRE(C % 8 == 0, "bn_act_apply: C=%d must be a multiple of 8", C);
     KP_REQUIRE(C <= 4096, "bn_act_apply: C=%d too large", C);
     const long long total = (long long)N * H * W * (C / 8);     // input vectors (one thread-item each)
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     const size_t smem = 2 * (size_t)C * sizeof(float);
-    if (upsample) bn_act_apply_kernel<true><<<grid_for(total, 256), 256, smem, st>>>(xi, scale, shift, relu, N, H, W, C, o);
-    else bn_act_apply_kernel<false><<<grid_for((total + 1) / 2, 256), 256, smem, st>>>(xi, scale, shift, relu, N, H, W, C, o);
+    if (upsample) bn_act_apply_kernel<true><<<grid_for(total, 256), 256, smem, st>>>(xi, scale, shift, fin, relu, N, H, W, C, o);
+    else bn_act_apply_kernel<false><<<grid_for((total + 1) / 2, 256), 256, smem, st>>>(xi, scale, shift, fin, relu, N, H, W, C, o);
     KP_LAUNCHED();
     return KP_OK;
+}
+int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
+                    void* out, cudaStream_t st) {
+    BnFin fin;
+    memset(&fin, 0, sizeof(fin));
+    return bn_apply_launch(x, scale, shift, fin, relu, upsample, N, H, W, C, out, st);
+}
+int ew_bn_stats_apply(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, double count,
+                      float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean, float* srstd,
+                      const void* x, int relu, int upsample, int N, int H, int W, int C, void* out, cudaStream_t st) {
+    BnFin fin = {ssum, ssq, bias, gamma, beta, (float)count, eps, decay, mm, mv, scale, shift, smean, srstd};
+    return bn_apply_launch(x, nullptr, nullptr, fin, relu, upsample, N, H, W, C, out, st);
 }
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
                   const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
@@ -850,6 +900,86 @@ pack_weights_dgrad_kernel(const float* __restrict__ w, kp_pack_desc d, __nv_bflo
         if (r < d.rows && d.c0 + r < d.cin && kc < d.cout) v = w[((long long)d.tap_flat[t] * d.cin + d.c0 + r) * d.cout + kc];
         dst[idx] = __float2bfloat16_rn(v);
     }
+}
+
+// ---- batched variant: one launch for a whole table of jobs (device memory) ----
+constexpr int PACK_DGRAD_PER_BLOCK = 256 * 16;
+
+__device__ __forceinline__ void pack_fwd_tile(const float* __restrict__ w, const kp_pack_desc& d, __nv_bfloat16* __restrict__ dst,
+                                              int bx, int by, int t, float (*tile)[33]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int kc0 = bx * 32, r0 = by * 32;
+    const float* wt = w + (long long)d.tap_flat[t] * d.cin * d.cout;
+    for (int i = ty; i < 32; i += 8) {
+        const int kc = kc0 + i, co = r0 + tx;
+        int ci = -1;
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+            if (s < d.nseg && kc >= d.seg_kbase[s] && kc - d.seg_kbase[s] < d.seg_count[s]) ci = d.seg_start[s] + kc - d.seg_kbase[s];
+        tile[i][tx] = (ci >= 0 && ci < d.cin && co < d.cout) ? wt[(long long)ci * d.cout + co] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int co = r0 + i, kc = kc0 + tx;
+        if (co < d.rows_pad && kc < d.Kper) dst[(long long)co * d.Ktot + (long long)t * d.Kper + kc] = __float2bfloat16_rn(tile[tx][i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const kp_pack_job* __restrict__ jobs, int n_jobs) {
+    __shared__ float tile[32][33];
+    __shared__ kp_pack_job job;
+    __shared__ int job_idx;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_jobs - 1;                 // last job with block_begin <= blockIdx.x
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        job_idx = lo;
+    }
+    __syncthreads();
+    {
+        const int* src = reinterpret_cast<const int*>(jobs + job_idx);
+        int* dstw = reinterpret_cast<int*>(&job);
+        for (int i = threadIdx.x; i < (int)(sizeof(kp_pack_job) / sizeof(int)); i += blockDim.x) dstw[i] = src[i];
+    }
+    __syncthreads();
+    const kp_pack_desc& d = job.d;
+    const int b = (int)blockIdx.x - job.block_begin;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(job.dst);
+    if (d.mode == 0) {
+        const int gx = (d.Kper + 31) / 32, gy = (d.rows_pad + 31) / 32;
+        const int t = b / (gx * gy), rem = b - t * gx * gy;
+        pack_fwd_tile(job.w, d, dst, rem % gx, rem / gx, t, tile);
+    } else {
+        const long long total = (long long)d.rows_pad * d.Ktot;
+        const long long base = (long long)b * PACK_DGRAD_PER_BLOCK;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const long long idx = base + i * 256 + threadIdx.x;
+            if (idx >= total) break;
+            const int r = (int)(idx / d.Ktot);
+            const int k = (int)(idx - (long long)r * d.Ktot);
+            const int t = k / d.Kper, kc = k - t * d.Kper;
+            float v = 0.f;
+            if (r < d.rows && d.c0 + r < d.cin && kc < d.cout) v = job.w[((long long)d.tap_flat[t] * d.cin + d.c0 + r) * d.cout + kc];
+            dst[idx] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+int ew_pack_job_blocks(const kp_pack_desc* d) {
+    if (d->mode == 0) return ((d->Kper + 31) / 32) * ((d->rows_pad + 31) / 32) * d->T;
+    const long long total = (long long)d->rows_pad * d->Ktot;
+    return (int)((total + PACK_DGRAD_PER_BLOCK - 1) / PACK_DGRAD_PER_BLOCK);
+}
+
+int ew_pack_weights_batch(const void* jobs_dev, int n_jobs, int total_blocks, cudaStream_t st) {
+    KP_REQUIRE(n_jobs > 0 && total_blocks > 0, "pack_weights_batch: empty table");
+    static_assert(sizeof(kp_pack_job) % sizeof(int) == 0, "kp_pack_job must be int-copyable");
+    pack_weights_batch_kernel<<<total_blocks, 256, 0, st>>>(reinterpret_cast<const kp_pack_job*>(jobs_dev), n_jobs);
+    KP_LAUNCHED();
+    return KP_OK;
 }
 
 int ew_pack_weights(const float* w, const kp_pack_desc* d, const float* row_scale, void* dst, cudaStream_t st) {

@@ -41,6 +41,17 @@ int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int r
     KP_REQUIRE((scale == nullptr) == (shift == nullptr), "%s: scale and shift go together", __func__);
     return ew_bn_act_apply(x, scale, shift, relu, upsample, N, H, W, C, out, ST);
 }
+int kp_bn_stats_apply(const float* stats_sum, const float* stats_sq, const float* conv_bias, const float* gamma,
+                      const float* beta, double count, float eps, float decay, float* moving_mean, float* moving_var,
+                      float* scale, float* shift, float* save_mean, float* save_rstd, const void* x, int relu, int upsample,
+                      int N, int H, int W, int C, void* out, void* stream) {
+    KP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && count > 0, "%s: bad shape", __func__);
+    KP_NONNULL(stats_sum); KP_NONNULL(stats_sq); KP_NONNULL(gamma); KP_NONNULL(beta); KP_NONNULL(scale); KP_NONNULL(shift);
+    KP_NONNULL(x); KP_NONNULL(out);
+    KP_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "%s: moving_mean and moving_var go together", __func__);
+    return ew_bn_stats_apply(stats_sum, stats_sq, conv_bias, gamma, beta, count, eps, decay, moving_mean, moving_var, scale,
+                             shift, save_mean, save_rstd, x, relu, upsample, N, H, W, C, out, ST);
+}
 int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
                   const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
                   void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, void* stream) {
@@ -118,6 +129,14 @@ int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float 
 int kp_pack_weights(const float* w, const kp_pack_desc* desc, const float* row_scale, void* dst, void* stream) {
     KP_NONNULL(w); KP_NONNULL(desc); KP_NONNULL(dst);
     return ew_pack_weights(w, desc, row_scale, dst, ST);
+}
+int kp_pack_job_blocks(const kp_pack_desc* desc) {
+    if (desc == nullptr || desc->T < 1 || desc->T > KP_MAX_TAPS || desc->Kper <= 0 || desc->Ktot != desc->T * desc->Kper) return 0;
+    return ew_pack_job_blocks(desc);
+}
+int kp_pack_weights_batch(const void* jobs_dev, int n_jobs, int total_blocks, void* stream) {
+    KP_NONNULL(jobs_dev);
+    return ew_pack_weights_batch(jobs_dev, n_jobs, total_blocks, ST);
 }
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream) {
     KP_NONNEG(P);

@@ -32,6 +32,9 @@ int ew_image_prep_bwd(const void* g, long long P, const float* a, const int* per
 int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, int C,
                    double count, float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean,
                    float* srstd, cudaStream_t st);
+int ew_bn_stats_apply(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, double count,
+                      float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean, float* srstd,
+                      const void* x, int relu, int upsample, int N, int H, int W, int C, void* out, cudaStream_t st);
 int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
                     void* out, cudaStream_t st);
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
@@ -53,6 +56,8 @@ int ew_bce_logits(const float* x, int n, float z, float weight, float* loss, voi
 int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int t,
                float grad_scale, const float* lr_t_dev, cudaStream_t st);
 int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st);
+int ew_pack_job_blocks(const kp_pack_desc* d);
+int ew_pack_weights_batch(const void* jobs_dev, int n_jobs, int total_blocks, cudaStream_t st);
 int ew_pack_weights(const float* w, const kp_pack_desc* d, const float* row_scale, void* dst, cudaStream_t st);
 int ew_image_prep_unrolled(const float* x, int N, int H, int W, int KW, int pl, int cpad, const float* a, const float* b,
                            const int* perm, void* out, cudaStream_t st);

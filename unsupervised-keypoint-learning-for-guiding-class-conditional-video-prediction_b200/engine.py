@@ -117,6 +117,8 @@ class Context:
         self.zoff = 0
         self._plans = {}
         self._packed = {}
+        self._jobs = {}        # id(group) -> [(key, plan, fp32 kernel view, packed bf16 tensor)]: re-packed in ONE launch
+        self._tables = {}      # id(group) -> (number of jobs when built, cv.PackTable)
 
     # ---- pooled zero-initialised scratch (BN statistics, per-call gradient sums): ONE memset per run ----
     ZPOOL_FLOATS = 4 * 1024 * 1024
@@ -154,11 +156,28 @@ class Context:
     def params_changed(self, group=None):
         """Invalidate packed-weight caches: all of them, or only those built from `group`'s variables."""
         self.version += 1
-        if group is None:
-            self._packed.clear()
-            return
-        for key in [k for k in self._packed if isinstance(k[1], tuple) and k[1] and k[1][0] in group]:
-            del self._packed[key]
+        groups = [group] if group is not None else [self.G, self.D, self.S, self.V]
+        keep = set()
+        for g in groups:
+            keep.update(j[0] for j in self._jobs.get(id(g), []))
+        for key in list(self._packed):
+            if key in keep:
+                continue
+            if group is None or (isinstance(key[1], tuple) and key[1] and key[1][0] in group):
+                del self._packed[key]
+        for g in groups:
+            jobs = self._jobs.get(id(g), [])
+            if not jobs:
+                continue
+            # re-pack every registered kernel of this optimiser in place, now, with one launch (the packed tensors keep
+            # their addresses: a captured CUDA graph keeps reading them)
+            built = self._tables.get(id(g))
+            if built is None or built[0] != len(jobs):
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("pack table changed during CUDA-graph capture (run two eager steps first)")
+                built = (len(jobs), cv.PackTable([(pl, w, out) for _, pl, w, out in jobs], self.device))
+                self._tables[id(g)] = built
+            built[1].run()
 
     def load_state_dict(self, sd):
         """sd: name -> tensor/ndarray (HWIO kernels).  Unknown names are ignored, like BaseModel.restore."""
@@ -188,6 +207,19 @@ class Context:
         if key not in self._packed:
             self._packed[key] = builder()
         return self._packed[key]
+
+    def packed_weight(self, kind, wnames, plan, w):
+        """bf16 packed copy of the kernel `w` for `plan`.  A kernel that is a plain view of ONE variable is registered
+        for the batched in-place re-pack that params_changed(group) runs; fused kernels (several variables
+        concatenated) are rebuilt on demand."""
+        key = (kind, tuple(wnames), tc.pack_key(plan))
+        out = self._packed.get(key)
+        if out is None:
+            out = cv.pack_weights(plan, w)
+            self._packed[key] = out
+            if len(wnames) == 1:
+                self._jobs.setdefault(id(self.group_of(wnames[0])), []).append((key, plan, w, out))
+        return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -228,9 +260,8 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
     cin_real = w.shape[2]
     cin_src = sum(s[3] for s in shapes)
     flop_scale = w.shape[2] / float(cin_src)      # algorithmic-FLOP accounting ignores zero-padded channels
-    if cin_src > w.shape[2]:
-        # sources carry zero-padded channels (3-channel images stored as 16, the 208-channel joint embedding as 256)
-        w = torch.nn.functional.pad(w, (0, 0, 0, cin_src - w.shape[2]))
+    # Sources may carry zero-padded channels (3-channel images stored as 16, the 208-channel joint embedding as 256)
+    # and Cout is padded to the channel block: the pack kernels zero-fill everything outside the real [cin, cout].
     fplan, (N, Ho, Wo) = ctx.plan("fwd", (shapes, k, stride, pad, cout), lambda: tc.plan_conv_fwd(list(shapes), k, stride, pad, cout))
     fplan.flop_scale = flop_scale
     dev = ctx.device
@@ -251,7 +282,7 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
             y = ops.bn_act_apply(y, None, None, relu=False, upsample=True)
         return y
 
-    wp = ctx.packed(("fwd", wkey, shapes), lambda: cv.pack_weights(fplan, w))
+    wp = ctx.packed_weight("fwd", wnames, fplan, w)
     bias = ctx.packed(("bias", wkey, fplan.rows_pad), lambda: _bias_vec(ctx, bnames, fplan.rows_pad))
 
     if bn is not None:
@@ -262,9 +293,8 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
         cv.run_plan(fplan, srcs, wp, bias, y_pre, act=tc.ACT_NONE, stats=(ssum, ssq))
         mm = ctx.p(bn + "/moving_mean") if ctx.update_moving else None
         mv = ctx.p(bn + "/moving_variance") if ctx.update_moving else None
-        scale, shift, mean, rstd = ops.bn_finalize(ssum, ssq, bias, ctx.p(bn + "/gamma"), ctx.p(bn + "/beta"),
-                                                   N * Ho * Wo, mm, mv)
-        out = ops.bn_act_apply(y_pre, scale, shift, relu=True, upsample=upsample)
+        out, scale, shift, mean, rstd = ops.bn_stats_apply(y_pre, ssum, ssq, bias, ctx.p(bn + "/gamma"), ctx.p(bn + "/beta"),
+                                                           N * Ho * Wo, mm, mv, relu=True, upsample=upsample)
         if ctx.debug is not None:
             ctx.debug[wnames[0].replace("/conv2d/kernel", "")] = (out, y_pre, scale, shift, mean, rstd, upsample)
         if ctx.tape is not None:
@@ -342,7 +372,6 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
                 o += co
     if not need_input_grad:
         return
-    wpad = w if cpad == cout else torch.nn.functional.pad(w, (0, cpad - cout))
     c0 = 0
     for s, shp in zip(srcs, shapes):
         C = shp[3]
@@ -351,6 +380,6 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
         dx, acc = tape.acquire(s)
         for i, p in enumerate(plans):
             p.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
-            wp = ctx.packed(("dgrad", tuple(wnames), shp, c0, cpad, i), lambda p=p: cv.pack_weights(p, wpad))
+            wp = ctx.packed_weight("dgrad", wnames, p, w)
             cv.run_plan(p, [dy], wp, None, dx, accumulate=acc)
         c0 += C

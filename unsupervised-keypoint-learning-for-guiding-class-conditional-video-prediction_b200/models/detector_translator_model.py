@@ -231,17 +231,20 @@ class DetectorTranslatorModel(BaseModel):
             snap = (self.ctx.G.data.clone(), self.ctx.D.data.clone(), self.ctx.S.data.clone(), self.t_D, self.t_G,
                     self.global_step.value, self.ctx.G.m.clone(), self.ctx.G.v.clone(), self.ctx.D.m.clone(),
                     self.ctx.D.v.clone())
-            self._run_D(self._static[0], self._static[1])
-            self._run_G(self._static[2], self._static[3])
+            for _ in range(2):              # step 1 registers every weight-pack job, step 2 builds the final job tables
+                self._run_D(self._static[0], self._static[1])
+                self._run_G(self._static[2], self._static[3])
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.ctx.params_changed()           # every weight re-pack must be recorded inside the graph
+        from .. import _lib
+        n0 = _lib.load().kp_launch_count()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             lD = self._run_D(self._static[0], self._static[1])
             lG = self._run_G(self._static[2], self._static[3])
+        self.graph_launches = int(_lib.load().kp_launch_count() - n0)   # library kernels recorded per replay
         self._graph_losses = (lD, lG)
-        # undo the two warm-up/capture steps' host-side bookkeeping and parameter updates
+        # undo the warm-up/capture steps' host-side bookkeeping and parameter updates
         self.ctx.G.data.copy_(snap[0]); self.ctx.D.data.copy_(snap[1]); self.ctx.S.data.copy_(snap[2])
         self.ctx.G.m.copy_(snap[6]); self.ctx.G.v.copy_(snap[7]); self.ctx.D.m.copy_(snap[8]); self.ctx.D.v.copy_(snap[9])
         self.t_D, self.t_G, self.global_step.value = snap[3], snap[4], snap[5]

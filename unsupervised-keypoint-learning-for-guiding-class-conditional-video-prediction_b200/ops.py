@@ -80,6 +80,19 @@ def bn_finalize(ssum, ssq, bias, gamma, beta, count, moving_mean, moving_var, ep
     return scale, shift, mean, rstd
 
 
+def bn_stats_apply(x, ssum, ssq, bias, gamma, beta, count, moving_mean, moving_var, relu=True, upsample=False, eps=1e-5,
+                   decay=0.999):
+    """bn_finalize + bn_act_apply in one launch -> (out, scale, shift, mean, rstd)."""
+    N, H, W, C = x.shape
+    dev = x.device
+    par = torch.empty((4, C), device=dev, dtype=F32)
+    out = torch.empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C), device=dev, dtype=BF16)
+    _lib.call("kp_bn_stats_apply", _p(ssum), _p(ssq), _p(bias), _p(gamma), _p(beta), float(count), eps, decay,
+              _p(moving_mean), _p(moving_var), _p(par[0]), _p(par[1]), _p(par[2]), _p(par[3]), _p(x), 1 if relu else 0,
+              1 if upsample else 0, N, H, W, C, _p(out), _st())
+    return out, par[0], par[1], par[2], par[3]
+
+
 def bn_act_apply(x, scale, shift, relu=True, upsample=False):
     N, H, W, C = x.shape
     out = torch.empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C), device=x.device, dtype=BF16)

@@ -322,6 +322,20 @@ class PackDesc(ctypes.Structure):
                 ("Kper", ctypes.c_int), ("rows_pad", ctypes.c_int), ("Ktot", ctypes.c_int)]
 
 
+class PackJob(ctypes.Structure):
+    """kp_pack_job: one entry of the device job table of kp_pack_weights_batch."""
+    _fields_ = [("w", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("d", PackDesc), ("block_begin", ctypes.c_int),
+                ("n_blocks", ctypes.c_int)]
+
+
+def pack_key(plan):
+    """What the packed layout depends on (NOT the batch / image size): convolutions of the same variable at different
+    batch sizes (img_discr on [real;fake] and on fake alone) share one packed copy."""
+    pk = plan.pack
+    extra = tuple(tuple(s) for s in pk["segs"]) if pk["mode"] == "fwd" else tuple(pk["row_slice"])
+    return (pk["mode"], tuple(pk["taps"]), extra, plan.rows_pad, plan.Ktot, plan.CB)
+
+
 def pack_desc(plan, w_shape):
     """Descriptor of the device weight re-layout for `plan` and an HWIO kernel of shape w_shape (same recipe as
     pack_weights_np)."""
