@@ -95,6 +95,17 @@ PERF = {
     "head_128_16_40": (32, 128, 128, [16], 1, 1, 40),
     "det_128_48_16": (32, 128, 128, [16, 32], 3, 1, 16),
     "vggfirst_128_16_64": (64, 128, 128, [16], 3, 1, 64),
+    # W-packed equivalents (P pixels folded into channels): what a 16->16 / 32->32 / 48->16 / head layer would cost
+    "packed4_16_16": (32, 128, 32, [64], 3, 1, 64),
+    "packed2_32_32": (32, 128, 64, [64], 3, 1, 64),
+    "packed4_48_16": (32, 128, 32, [64, 128], 3, 1, 64),
+    "packed4_head": (32, 128, 32, [64], 1, 1, 160),
+    "packed2_32_32_64sq": (32, 64, 32, [64], 3, 1, 64),
+    "det_64_32": (32, 64, 64, [32], 3, 1, 32),
+    "heads_128_64_8": (32, 128, 128, [64], 3, 1, 8),
+    "enc1_128_32_32_7x1": (32, 128, 128, [32], (7, 1), 1, 32),
+    "dec_64_96_32": (32, 64, 64, [32, 64], 3, 1, 32),
+    "dec_64_32_32": (32, 64, 64, [32], 3, 1, 32),
 }
 
 
@@ -110,14 +121,15 @@ def run_perf():
             continue
         xs = [torch.randn((N, H, W, C), device=dev).to(torch.bfloat16) for C in Cs]
         cin = sum(Cs)
-        w = torch.randn((k, k, cin, cout), device=dev) / (k * k * cin) ** 0.5
+        kh, kw = (k, k) if isinstance(k, int) else k
+        w = torch.randn((kh, kw, cin, cout), device=dev) / (kh * kw * cin) ** 0.5
         plan, (n, ho, wo) = tc.plan_conv_fwd([tuple(x.shape) for x in xs], k, s, 0, cout)
         wp = conv.pack_weights(plan, w)
         out = torch.empty((n, ho, wo, cout), device=dev, dtype=torch.bfloat16)
         bias = torch.zeros(plan.rows_pad, device=dev)
         dy = torch.randn((n, ho, wo, cout), device=dev).to(torch.bfloat16)
         wplan = tc.plan_conv_wgrad(tuple(xs[0].shape), k, s, 0, cout, cin_slice=(0, Cs[0], cin) if len(Cs) > 1 else None)
-        dw = torch.zeros((k, k, cin, cout), device=dev)
+        dw = torch.zeros((kh, kw, cin, cout), device=dev)
 
         def timeit(fn, reps=reps_env):
             for _ in range(3 if reps > 1 else 1):
@@ -141,7 +153,7 @@ def run_perf():
             extra["fwd_nobias_noact_ms"] = timeit(lambda: conv.run_plan(plan, xs, wp, None, out))
             extra["fwd_f32_ms"] = timeit(lambda: conv.run_plan(plan, xs, wp, bias, out32))
         t_w = timeit(lambda: conv.run_wgrad(wplan, xs[0], dy, dw))
-        flop = 2.0 * n * ho * wo * k * k * cin * cout
+        flop = 2.0 * n * ho * wo * kh * kw * cin * cout
         byt = 2.0 * (sum(x.numel() for x in xs) + out.numel())
         print(json.dumps({"perf": name, "fwd_ms": t_f, "fwd_tflops": flop / t_f / 1e9, "fwd_gbs_min": byt / t_f / 1e6,
                           "wgrad_ms": t_w, "wgrad_tflops": flop / t_w / 1e9, **extra}), flush=True)

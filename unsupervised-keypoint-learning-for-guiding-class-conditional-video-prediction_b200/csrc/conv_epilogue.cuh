@@ -1,0 +1,163 @@
+// Epilogue of the tap-GEMM convolution kernels, shared by the TMA-tap kernel (conv_tc.cu) and the halo-tile kernel
+// (conv_halo.cu): one 16-column chunk of one accumulator row (= one output pixel) held in registers.
+#pragma once
+#include "kp_tc.cuh"
+
+namespace kp {
+
+// 32 lanes x 16 columns -> per-column totals: lane l ends with the total of column
+// (bit4*8 + bit3*4 + bit2*2 + bit1) of l; 16 shuffles instead of 80.
+__device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
+    float a[8];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float keep = up ? v[j + 8] : v[j], send = up ? v[j] : v[j + 8];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    float b[4];
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float keep = up ? a[j + 4] : a[j], send = up ? a[j] : a[j + 4];
+            b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    float c[2];
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float keep = up ? b[j + 2] : b[j], send = up ? b[j] : b[j + 2];
+            c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    float d;
+    {
+        const bool up = lane & 2;
+        const float keep = up ? c[1] : c[0], send = up ? c[0] : c[1];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+// P: kernel parameter struct with the fields out, out_off (unused here), Cout, cout_pad, out_f32, act, accumulate, alpha,
+// bias, ssum, ssq, ksplit.  v: the 16 accumulator columns ch0..ch0+15 of this thread's pixel (all 32 lanes of the warp
+// must call: the statistics use warp shuffles); pix: element offset of the pixel in the output view; valid: the pixel
+// exists; ks: split-K index; s_bias / s_stat: the per-CTA shared-memory copies (bias [cout_pad], sums [2][cout_pad]).
+template <class P>
+__device__ __forceinline__ void epi_chunk(const P& p, float (&v)[16], const int ch0, const bool valid, const long long pix,
+                                          const int lane, const int ks, const float* s_bias, float* s_stat) {
+    if (p.ssum != nullptr) {
+        float sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+        const float s1 = warp_colsum16(v, lane);
+        const float s2 = warp_colsum16(sq, lane);
+        if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            atomicAdd(s_stat + ch0 + col, s1);
+            atomicAdd(s_stat + p.cout_pad + ch0 + col, s2);
+        }
+    }
+    // Everything below is fully unrolled with compile-time indices so v[] stays in registers, and the
+    // activation is selected by ONE warp-uniform branch per chunk (the first version indexed v[]
+    // dynamically -> local memory, and evaluated the activation switch per element: ~8000 instructions
+    // per warp per tile, which made the whole kernel epilogue-bound).
+    if (p.ksplit > 1) {
+        // split-K partial tile: fp32 atomic accumulation into the zeroed output (host guarantees f32 output,
+        // no activation); the bias is contributed once, by split 0
+        if (valid && ch0 < p.Cout) {
+            float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
+            const int nvalid = p.Cout - ch0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nvalid) atomicAdd(o + j, v[j] + ((ks == 0 && p.bias != nullptr) ? s_bias[ch0 + j] : 0.f));
+        }
+    } else if (valid && ch0 < p.Cout) {
+        if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + ch0);   // 64-byte aligned chunk, broadcast
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b = b4[j];
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+        }
+        if (p.act == KP_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == KP_ACT_LEAKY) {
+            const float al = p.alpha;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : al * v[j];
+        } else if (p.act == KP_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        } else if (p.act == KP_ACT_SIGMOID_LAST) {
+            const int last = p.Cout - 1 - ch0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j == last) v[j] = 1.f / (1.f + __expf(-v[j]));
+        }
+        const int nvalid = p.Cout - ch0;   // >= 1; the chunk is complete when >= 16
+        // Vector stores per group of 4 floats / 8 bf16 wherever the group is complete (Cout = 40 leaves a
+        // half chunk: scalar 2-byte stores at a 80-byte lane stride throttled the LSU), scalars for the rest.
+        if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
+            const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (al && 4 * j + 4 <= nvalid) {
+                    float4* o4 = reinterpret_cast<float4*>(o) + j;
+                    if (p.accumulate) {
+                        const float4 b = *o4;
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                    *o4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * j + e < nvalid) o[4 * j + e] = p.accumulate ? o[4 * j + e] + v[4 * j + e] : v[4 * j + e];
+                }
+            }
+        } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + ch0;
+            const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (al && 8 * h + 8 <= nvalid) {
+                    uint4* o4 = reinterpret_cast<uint4*>(o) + h;
+                    if (p.accumulate) {
+                        const uint4 u = *o4;
+                        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 a = __bfloat1622float2(hp[j]);
+                            v[8 * h + 2 * j] += a.x; v[8 * h + 2 * j + 1] += a.y;
+                        }
+                    }
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+                        w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    *o4 = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (8 * h + e < nvalid)
+                            o[8 * h + e] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[8 * h + e]) + v[8 * h + e]
+                                                                            : v[8 * h + e]);
+                }
+            }
+        }
+    }
+
+}
+
+}  // namespace kp

@@ -17,6 +17,7 @@
 // (ncu of the first, non-persistent version: tensor pipe 9-21 % active with DRAM/L2/L1 all far from saturated,
 //  i.e. bound by the serial prologue -> main loop -> epilogue chain of each tile; profiles/README.md.)
 #include "kp_tc.cuh"
+#include "conv_epilogue.cuh"
 #include "kp_internal.h"
 #include <cudaTypedefs.h>
 #include <string.h>
@@ -52,46 +53,6 @@ __device__ __forceinline__ float apply_act(float x, int act, float alpha, bool l
         case KP_ACT_SIGMOID_LAST: return last ? 1.f / (1.f + __expf(-x)) : x;
         default: return x;
     }
-}
-
-// 32 lanes x 16 columns -> per-column totals: lane l ends with the total of column
-// (bit4*8 + bit3*4 + bit2*2 + bit1) of l; 16 shuffles instead of 80.
-__device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
-    float a[8];
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float keep = up ? v[j + 8] : v[j], send = up ? v[j] : v[j + 8];
-            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    float b[4];
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float keep = up ? a[j + 4] : a[j], send = up ? a[j] : a[j + 4];
-            b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    float c[2];
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float keep = up ? b[j + 2] : b[j], send = up ? b[j] : b[j + 2];
-            c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    float d;
-    {
-        const bool up = lane & 2;
-        const float keep = up ? c[1] : c[0], send = up ? c[0] : c[1];
-        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    return d;
 }
 
 template <int CB>
@@ -175,7 +136,8 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         }
     } else if (warp == 1) {
         // ------------------------------- MMA issuer -------------------------------
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one() ? 1u : 0u;
             const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
             uint32_t git = 0;
             int lt = 0;
@@ -201,12 +163,12 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                             // the 16-element slice of block g / step k sits (g*CB + k*16)*2 bytes into the row
                             const uint64_t da = umma_smem_desc(a_addr + g * A_BOX_BYTES + k * 32, SBO, 16, LAYOUT);
                             const uint64_t db = umma_smem_desc(b_addr + (g * CB + k * 16) * 2, 1024, 16, 2u);
-                            umma_bf16(d_tmem, da, db, idesc, ((it0 - it_begin) | g | k) != 0 ? 1u : 0u);
+                            umma_bf16_if(leader, d_tmem, da, db, idesc, ((it0 - it_begin) | g | k) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty[st]);
+                    umma_commit_if(leader, &empty[st]);
                 }
-                umma_commit(&tfull[acc]);
+                umma_commit_if(leader, &tfull[acc]);
             }
         }
     } else {
@@ -247,112 +209,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                const int ch0 = n_off + c0;
-                if (p.ssum != nullptr) {
-                    float sq[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-                    const float s1 = warp_colsum16(v, lane);
-                    const float s2 = warp_colsum16(sq, lane);
-                    if ((lane & 1) == 0) {
-                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(s_stat + ch0 + col, s1);
-                        atomicAdd(s_stat + p.cout_pad + ch0 + col, s2);
-                    }
-                }
-                // Everything below is fully unrolled with compile-time indices so v[] stays in registers, and the
-                // activation is selected by ONE warp-uniform branch per chunk (the first version indexed v[]
-                // dynamically -> local memory, and evaluated the activation switch per element: ~8000 instructions
-                // per warp per tile, which made the whole kernel epilogue-bound).
-                if (p.ksplit > 1) {
-                    // split-K partial tile: fp32 atomic accumulation into the zeroed output (host guarantees f32 output,
-                    // no activation); the bias is contributed once, by split 0
-                    if (valid && ch0 < p.Cout) {
-                        float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
-                        const int nvalid = p.Cout - ch0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < nvalid) atomicAdd(o + j, v[j] + ((ks == 0 && p.bias != nullptr) ? s_bias[ch0 + j] : 0.f));
-                    }
-                } else if (valid && ch0 < p.Cout) {
-                    if (p.bias != nullptr) {
-                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + ch0);   // 64-byte aligned chunk, broadcast
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = b4[j];
-                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                        }
-                    }
-                    if (p.act == KP_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (p.act == KP_ACT_LEAKY) {
-                        const float al = p.alpha;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : al * v[j];
-                    } else if (p.act == KP_ACT_SIGMOID) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-                    } else if (p.act == KP_ACT_SIGMOID_LAST) {
-                        const int last = p.Cout - 1 - ch0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j == last) v[j] = 1.f / (1.f + __expf(-v[j]));
-                    }
-                    const int nvalid = p.Cout - ch0;   // >= 1; the chunk is complete when >= 16
-                    // Vector stores per group of 4 floats / 8 bf16 wherever the group is complete (Cout = 40 leaves a
-                    // half chunk: scalar 2-byte stores at a 80-byte lane stride throttled the LSU), scalars for the rest.
-                    if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
-                        const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (al && 4 * j + 4 <= nvalid) {
-                                float4* o4 = reinterpret_cast<float4*>(o) + j;
-                                if (p.accumulate) {
-                                    const float4 b = *o4;
-                                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                                }
-                                *o4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (4 * j + e < nvalid) o[4 * j + e] = p.accumulate ? o[4 * j + e] + v[4 * j + e] : v[4 * j + e];
-                            }
-                        }
-                    } else {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix + ch0;
-                        const bool al = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (al && 8 * h + 8 <= nvalid) {
-                                uint4* o4 = reinterpret_cast<uint4*>(o) + h;
-                                if (p.accumulate) {
-                                    const uint4 u = *o4;
-                                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const float2 a = __bfloat1622float2(hp[j]);
-                                        v[8 * h + 2 * j] += a.x; v[8 * h + 2 * j + 1] += a.y;
-                                    }
-                                }
-                                uint32_t w[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
-                                    w[j] = *reinterpret_cast<uint32_t*>(&h2);
-                                }
-                                *o4 = make_uint4(w[0], w[1], w[2], w[3]);
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 8; ++e)
-                                    if (8 * h + e < nvalid)
-                                        o[8 * h + e] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[8 * h + e]) + v[8 * h + e]
-                                                                                        : v[8 * h + e]);
-                            }
-                        }
-                    }
-                }
+                epi_chunk(p, v, n_off + c0, valid, pix, lane, ks, s_bias, s_stat);
             }
         }
         if (p.ssum != nullptr) {
@@ -463,6 +320,8 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     KP_REQUIRE((ssum == nullptr) == (ssq == nullptr), "kp_tapconv: stats_sum and stats_sq go together");
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return KP_ERR_DRIVER;
+    // stride-1 multi-tap layers: halo-tile kernel (each input element is fetched once per tile instead of once per tap)
+    if (haloconv_eligible(d, ssum)) return haloconv_launch(d, src, wpacked, bias, out, ssum, ssq, st);
 
     TapConvKParams p;
     memset(&p, 0, sizeof(p));

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const uint32_t leader = elect_one() ? 1u : 0u;   // warp-uniform loop, one elected lane issues (see kp_tc.cuh)
             const uint32_t idesc = umma_idesc_bf16(128, p.BN, 1, 1);  // both operands MN-major
             for (int it = 0; it < n_iters; ++it) {
                 const int st = it % S;
@@ -127,12 +128,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                     for (int kk = 0; kk < KP / 16; ++kk) {
                         const uint64_t da = umma_smem_desc(x_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
                         const uint64_t db = umma_smem_desc(dy_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
-                        umma_bf16(d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
+                        umma_bf16_if(leader, d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
                     }
                 }
-                umma_commit(&empty[st]);
+                umma_commit_if(leader, &empty[st]);
             }
-            umma_commit(tfull);
+            umma_commit_if(leader, tfull);
         }
     } else {
         const int q = warp & 3;

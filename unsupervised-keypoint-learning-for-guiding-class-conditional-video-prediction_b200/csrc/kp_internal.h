@@ -20,6 +20,9 @@ int k1_render_colorize(const float* mu, const float* colors, int B, int K, int h
 int k1_colorize(const float* maps, const float* colors, long long P, int K, float* out, cudaStream_t st);
 
 // conv_tc.cu
+bool haloconv_eligible(const kp_tapconv_desc* d, const float* ssum);
+int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
+                    float* ssum, float* ssq, cudaStream_t st);
 int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
                    float* ssum, float* ssq, cudaStream_t st);
 
