@@ -207,17 +207,29 @@ def run_reference(args):
         sample = ("%d train_steps (D run + G run, fwd+bwd incl. VGG19, TF Adam) at batch %d instead of 32: torch-CPU fp32 "
                   "oracle of the reference graph, %d threads" % (steps, b, cores))
         metric, wl, ms = "stage-1 frames/sec (train_step: D run + G run)", "train", sec * 1e3
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": wl, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 # --------------------------------------------------------------------------------------------------
 # GPU arms
 # --------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def _dist_setup():
     import torch
     import torch.distributed as dist
@@ -304,11 +316,11 @@ def run_ours(args):
     if args.workload == "k1":
         r = bench_k1(args, world, rank, dev, lib)
         if rank == 0:
-            print(json.dumps({"metric": "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "value": r["frames_per_s"],
+            emit({"metric": "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "value": r["frames_per_s"],
                               "unit": "frames/s", "n_gpus": world, "steps": r["steps"], "warmup": args.warmup,
                               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                               "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"]},
-                              "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]}), flush=True)
+                              "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]})
         if world > 1:
             torch.distributed.barrier()
             os._exit(0)
@@ -379,9 +391,10 @@ def run_ours(args):
 
     # ---- conv-kernel-only tensor throughput: one eager step with CUDA events around every conv launch ----
     kern = None
-    if rank == 0 and not args.no_kernel_profile:
+    if not args.no_kernel_profile:
+        # every rank runs the eager step (it contains the gradient all-reduces); only rank 0 records and reports
         from kp_b200 import conv as cv
-        cv.PROFILE = []
+        cv.PROFILE = [] if rank == 0 else None
         saved = model._graph
         model._graph = None
         # The eager step is CPU-launch bound; park the GPU behind a long spin kernel so that the whole step is queued
@@ -390,18 +403,19 @@ def run_ours(args):
         model.train_step()
         torch.cuda.synchronize()
         model._graph = saved
-        if os.environ.get("KP_BENCH_CONV_DETAIL"):
+        if rank == 0 and os.environ.get("KP_BENCH_CONV_DETAIL"):
             rows = sorted(((e0.elapsed_time(e1), kind, f, tag) for kind, f, e0, e1, tag in cv.PROFILE), reverse=True)
             for ms_, kind, f, tag in rows[:int(os.environ.get("KP_BENCH_CONV_DETAIL_ROWS", "60"))]:
                 sys.stderr.write("conv %-6s %8.1f us %8.1f GFLOP %7.1f TFLOP/s  %s\n" % (kind, ms_ * 1e3, f / 1e9, f / (ms_ * 1e-3) / 1e12, tag))
-        tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in cv.PROFILE)
-        tot_fl = sum(f for _, f, _, _, _ in cv.PROFILE)
-        by = {}
-        for kind, f, e0, e1, _ in cv.PROFILE:
-            a = by.setdefault(kind, [0.0, 0.0, 0])
-            a[0] += f; a[1] += e0.elapsed_time(e1); a[2] += 1
-        kern = {"conv_launches": len(cv.PROFILE), "conv_ms": tot_ms, "conv_tflops": tot_fl / (tot_ms * 1e-3) / 1e12,
-                "by_kind": {k: {"launches": v[2], "ms": v[1], "tflops": v[0] / (v[1] * 1e-3) / 1e12} for k, v in by.items()}}
+        if rank == 0:
+            tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in cv.PROFILE)
+            tot_fl = sum(f for _, f, _, _, _ in cv.PROFILE)
+            by = {}
+            for kind, f, e0, e1, _ in cv.PROFILE:
+                a = by.setdefault(kind, [0.0, 0.0, 0])
+                a[0] += f; a[1] += e0.elapsed_time(e1); a[2] += 1
+            kern = {"conv_launches": len(cv.PROFILE), "conv_ms": tot_ms, "conv_tflops": tot_fl / (tot_ms * 1e-3) / 1e12,
+                    "by_kind": {k: {"launches": v[2], "ms": v[1], "tflops": v[0] / (v[1] * 1e-3) / 1e12} for k, v in by.items()}}
         cv.PROFILE = None
 
     k1r = None if args.no_k1 else bench_k1(args, world, rank, dev, lib)
@@ -444,7 +458,7 @@ def run_ours(args):
         }
         if k1r is not None:
             line["k1"] = k1r
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Tear down in a safe order: drop the captured graph (it holds NCCL kernels) before the communicator goes,
         # and leave through os._exit so that no destructor can block on a peer that is already gone.
@@ -474,6 +488,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL's version banner, nvcc, pytest plugins)
+    # are sent to stderr for the whole run, the result goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
