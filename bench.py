@@ -11,6 +11,10 @@ Workloads
          40 keypoints, frame-batch data parallel with one NCCL all-reduce per optimiser.  A step consumes
          4*32 frames per GPU (2 batches x (image, future_image)).
   k1     BASELINE.json configs[1] — fused soft-argmax + Gaussian render micro-bench, 1024 frames per GPU.
+  pseudo BASELINE.json configs[3] — make_pseudo_labels: KeypointModel (detector only, inference BN) over the rank's
+         shard of the frame list, no collective; a step = --pseudo-frames frames per GPU.
+  render BASELINE.json configs[4] — evaluate-style rendering: FinalModel turns 64 first frames + 64 synthetic
+         32-step keypoint trajectories per GPU into 64 x 32 frames (translator, inference BN).
 The default run measures `train` and appends the k1 roofline as `"k1": {...}` (a few extra seconds).
 """
 import argparse
@@ -265,6 +269,98 @@ def _max_over_ranks(x, world, dev):
     return float(t.item())
 
 
+def bench_inference(args, world, rank, dev, lib, peaks):
+    """pseudo / render workloads: sharded over ranks with no collective."""
+    import torch
+    from kp_b200 import models, conv as cv
+    cfg = json.loads(json.dumps(CONFIG))
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    if args.workload == "pseudo":
+        F = args.pseudo_frames
+        model = models.KeypointModel(cfg, device=dev)
+        frames = [torch.rand((F, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)]   # 2 x 805 MB at F=4096
+        host = [f.cpu().pin_memory() for f in frames]
+        run_dev = lambda i: model.detect(frames[i % 2])
+        run_host = lambda i: model.detect(host[i % 2].to(dev, non_blocking=True)).cpu()
+        units, h2d, d2h = F, F * 128 * 128 * 3 * 4, F * 40 * 2 * 4
+        metric = "stage-1 frames/sec (make_pseudo_labels: detector-only pass)"
+        wl = ("BASELINE configs[3]: KeypointModel.detect over %d synthetic frames per GPU per step (the rank's shard of the frame "
+              "list, no collective), inference-mode BN folded into the convolutions, random-init" % F)
+    else:
+        V, T = args.render_videos, 32
+        model = models.FinalModel(cfg, device=dev)
+        ims = [torch.rand((V, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)]
+        seqs = [torch.rand((V, T, 40, 2), device=dev, generator=gen) * 1.6 - 0.8 for _ in range(2)]
+        host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in zip(ims, seqs)]
+
+        def run_dev(i):
+            model.build({"image": ims[i % 2], "pred_seq": seqs[i % 2]})
+            return model.run(visualize=False)["pred_im_seq"]
+
+        def run_host(i):
+            a, b = host[i % 2]
+            model.build({"image": a.to(dev, non_blocking=True), "pred_seq": b.to(dev, non_blocking=True)})
+            return model.run(visualize=False)["pred_im_seq"].cpu()
+        units, h2d, d2h = V * T, V * 128 * 128 * 3 * 4 + V * T * 40 * 2 * 4, V * T * 128 * 128 * 3 * 4
+        metric = "stage-1 frames/sec (evaluate-style rendering: translator over keypoint trajectories)"
+        wl = ("BASELINE configs[4]: FinalModel.run on %d videos per GPU per step: image_encoder + pose_encoder on the first frame, "
+              "%d-step synthetic trajectories -> Gaussian maps -> translator -> mask compose; %d frames per step, random-init"
+              % (V, T, V * T))
+    for i in range(args.warmup):
+        run_dev(i)
+    _barrier(world)
+    sampler = ClockSampler(dev.index or 0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.kp_launch_count()
+    sampler.start()
+    ev0.record()
+    for i in range(args.steps):
+        run_dev(i)
+    ev1.record()
+    _barrier(world)
+    clocks = sampler.stop()
+    launches = int(lib.kp_launch_count() - n0)
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world, dev) / args.steps
+    value = world * units / (ms * 1e-3)
+    e2e_steps = max(3, min(args.steps, 10))
+    run_host(0)
+    _barrier(world)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        run_host(i)
+    _barrier(world)
+    e2e_value = world * units * e2e_steps / _max_over_ranks(time.perf_counter() - t0, world, dev)
+    cv.PROFILE = []
+    torch.cuda._sleep(int(2e8))
+    run_dev(0)
+    torch.cuda.synchronize()
+    tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in cv.PROFILE)
+    tot_fl = sum(f for _, f, _, _, _ in cv.PROFILE)
+    n_conv = len(cv.PROFILE)
+    cv.PROFILE = None
+    if rank == 0:
+        peak = peaks["bf16_tflops_sustained"]
+        achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+        emit({"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+              "data": "synthetic",
+              "config": {"workload": wl, "frames_per_step_per_gpu": units, "parallelism": "dp%d (sharded, no collective)" % world,
+                         "l2": "inputs of a step (>= 400 MB) >> 126 MB L2; two input sets alternate"},
+              "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                           "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                           "kernel": "kp::tapconv_kernel / kp::haloconv_kernel (all %d conv launches of one step, CUDA events per "
+                                     "launch)" % n_conv,
+                           "algorithmic_flops_per_step": tot_fl, "conv_ms": tot_ms,
+                           "whole_step_tflops": tot_fl / (ms * 1e-3) / 1e12},
+              "cpu_baseline": None,
+              "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "steps": e2e_steps, "note": "pinned host inputs -> H2D -> model -> results D2H, every step"},
+              "gpu_launches": launches, "clocks": clocks})
+    if world > 1:
+        torch.distributed.barrier()
+        os._exit(0)
+
+
 def bench_k1(args, world, rank, dev, lib):
     import torch
     from kp_b200 import k1
@@ -324,6 +420,10 @@ def run_ours(args):
         if world > 1:
             torch.distributed.barrier()
             os._exit(0)
+        return
+
+    if args.workload in ("pseudo", "render"):
+        bench_inference(args, world, rank, dev, lib, peaks)
         return
 
     # ------------------------------ train workload ------------------------------
@@ -475,11 +575,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="train", choices=["train", "k1"])
+    ap.add_argument("--workload", default="train", choices=["train", "k1", "pseudo", "render"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="train: pairs per GPU per run")
     ap.add_argument("--frames", type=int, default=1024, help="k1: frames per GPU per launch")
     ap.add_argument("--k1-steps", type=int, default=100)
+    ap.add_argument("--pseudo-frames", type=int, default=4096, help="pseudo: frames per GPU per step")
+    ap.add_argument("--render-videos", type=int, default=64, help="render: videos per GPU per step (32 frames each)")
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true")

@@ -372,3 +372,60 @@ def test_w_unrolled_first_layer_matches_square_conv(cuda_dev, k, cpad, cout, wit
     for c in range(3):
         ref_dimg[..., perm[c]] += pre_img.grad[..., c] * a_[c]
     _close(dimg, ref_dimg, 1.5e-2, "d_image")
+
+
+HALO_CASES = [
+    # (N,H,W,[C],k,cout,out_f32,stats)  - every branch of csrc/conv_halo.cu
+    (2, 32, 32, [64], 3, 64, False, False),        # halves=2, weights resident
+    (2, 32, 32, [256], 3, 256, False, True),       # streamed weight stages, two channel tiles, BN statistics
+    (2, 16, 16, [128], 3, 384, False, False),      # halves=1, BN=128 x 3 channel tiles
+    (3, 24, 20, [16, 32], 3, 16, False, True),     # ragged H/W, virtual concat, statistics with invalid pixels
+    (1, 32, 32, [8], 3, 8, False, False),          # 8-channel slot (zero-filled second plane), dgrad of a 1-ch head
+    (2, 32, 24, [40], 3, 40, True, False),         # 32+8 channel slots, fp32 output, partial last chunk
+    (1, 64, 64, [32], (7, 1), 32, False, False),   # 7x1 taps (W-unrolled first layer), 38-row halo
+    (2, 128, 128, [16], 3, 16, False, False),      # the detector's 128x128 16-channel layers
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_halo_tile_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypatch):
+    """The halo-tile kernel is normally chosen for narrow outputs only; force it for every eligible shape and compare
+    with the fp64 conv oracle (<= 1e-2 of max|ref|, the bf16 conv tolerance) and with the TMA-tap kernel on the same
+    operands (both accumulate bf16 products in fp32: <= 2e-3 of max|ref|, differences are summation order + bf16 output
+    rounding)."""
+    from kp_b200 import conv, tapconv as tc
+    N, H, W, Cs, k, cout, out_f32, stats = case
+    kh, kw = (k, k) if isinstance(k, int) else k
+    rng = np.random.default_rng(N * 1000 + H + cout)
+    cin = sum(Cs)
+    xs = [torch.from_numpy(rng.normal(size=(N, H, W, C)).astype(np.float32)).to(BF) for C in Cs]
+    w = torch.from_numpy((rng.normal(size=(kh, kw, cin, cout)) / np.sqrt(kh * kw * cin)).astype(np.float32)).to(BF).float()
+    b = torch.from_numpy(rng.normal(0, 0.2, cout).astype(np.float32))
+    plan, (n, ho, wo) = tc.plan_conv_fwd([tuple(x.shape) for x in xs], k, 1, 0, cout)
+    srcs = [x.to(cuda_dev) for x in xs]
+    wp = conv.pack_weights(plan, w.to(cuda_dev))
+    bias = conv.pad_vec(b.to(cuda_dev), plan.rows_pad)
+    odt = torch.float32 if out_f32 else BF
+
+    def run(halo):
+        monkeypatch.setenv("KP_TAPCONV_HALO", "1" if halo else "0")
+        monkeypatch.setenv("KP_HALO_MAX_COUT", "4096")
+        out = torch.full((n, ho, wo, cout), float("nan"), device=cuda_dev, dtype=odt)
+        st = (torch.zeros(plan.rows_pad, device=cuda_dev), torch.zeros(plan.rows_pad, device=cuda_dev)) if stats else None
+        conv.run_plan(plan, srcs, wp, None if stats else bias, out, act=tc.ACT_NONE if stats else tc.ACT_RELU, stats=st)
+        torch.cuda.synchronize()
+        return out.float().cpu(), (None if st is None else (st[0].cpu(), st[1].cpu()))
+    y_halo, st_halo = run(True)
+    y_tap, st_tap = run(False)
+    ref = T.conv2d(torch.cat([x.double() for x in xs], dim=-1), w.double(), None if stats else b.double(), 1, 0)
+    if not stats:
+        ref = torch.relu(ref)
+    scale = ref.abs().max().item()
+    assert torch.isfinite(y_halo).all()
+    assert (y_halo.double() - ref).abs().max().item() <= 1e-2 * scale
+    assert (y_halo - y_tap).abs().max().item() <= 2e-3 * scale
+    if stats:
+        s_ref, q_ref = ref.sum(dim=(0, 1, 2)), (ref * ref).sum(dim=(0, 1, 2))
+        for got in (st_halo, st_tap):
+            assert (got[0][:cout].double() - s_ref).abs().max().item() <= 2e-3 * (s_ref.abs().max().item() + ref.abs().sum(dim=(0, 1, 2)).max().item() * 1e-2)
+            assert (got[1][:cout].double() - q_ref).abs().max().item() <= 2e-3 * q_ref.abs().max().item()

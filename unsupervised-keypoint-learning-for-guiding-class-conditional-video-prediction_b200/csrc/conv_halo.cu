@@ -367,7 +367,10 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     p.halves = d->Ho >= 32 ? 2 : 1;
     int BN = d->Cout_pad;
     const int bn_cap = p.halves == 2 ? 128 : 256;
-    if (BN > bn_cap) BN = bn_cap;
+    if (BN > bn_cap) {
+        BN = bn_cap;
+        while (BN > 16 && d->Cout_pad % BN != 0) BN >>= 1;
+    }
     KP_REQUIRE(BN % 16 == 0 && d->Cout_pad % BN == 0, "kp_tapconv(halo): Cout_pad=%d does not tile by %d", d->Cout_pad, BN);
     p.BN = BN;
     p.n_tiles = d->Cout_pad / BN;
