@@ -391,8 +391,8 @@ HALO_CASES = [
 def test_halo_tile_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypatch):
     """The halo-tile kernel is normally chosen for narrow outputs only; force it for every eligible shape and compare
     with the fp64 conv oracle (<= 1e-2 of max|ref|, the bf16 conv tolerance) and with the TMA-tap kernel on the same
-    operands (both accumulate bf16 products in fp32: <= 2e-3 of max|ref|, differences are summation order + bf16 output
-    rounding)."""
+    operands (both accumulate bf16 products in fp32; a different summation order can flip the bf16 rounding of an output by
+    one ulp = 2^-7 relative: <= 8e-3 of max|ref|)."""
     from kp_b200 import conv, tapconv as tc
     N, H, W, Cs, k, cout, out_f32, stats = case
     kh, kw = (k, k) if isinstance(k, int) else k
@@ -423,7 +423,7 @@ def test_halo_tile_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypa
     scale = ref.abs().max().item()
     assert torch.isfinite(y_halo).all()
     assert (y_halo.double() - ref).abs().max().item() <= 1e-2 * scale
-    assert (y_halo - y_tap).abs().max().item() <= 2e-3 * scale
+    assert (y_halo - y_tap).abs().max().item() <= 8e-3 * scale
     if stats:
         s_ref, q_ref = ref.sum(dim=(0, 1, 2)), (ref * ref).sum(dim=(0, 1, 2))
         for got in (st_halo, st_tap):

@@ -28,7 +28,7 @@ struct alignas(64) WgradKParams {
     signed char dh[KP_MAX_TAPS], dw[KP_MAX_TAPS], mf[KP_MAX_TAPS];
     int tap_flat[KP_MAX_TAPS];
     int TW, TH, TN, tiles_w, tiles_h, total_tiles, tiles_per_split;
-    int n_taps, T;                       // taps per CTA (group size)
+    int n_taps, T, R;                    // taps per CTA (group size); taps covered by ONE M=128 MMA (R > 1 when Cin <= 64)
     int Cin, Cout, BN, co_blocks, tmem_cols, stages;
     int n_a_max, n_b_max;
     uint32_t box_bytes, stage_bytes;
@@ -121,9 +121,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                 mbar_wait(&full[st], (it / S) & 1);
                 tc_fence_after();
                 const uint32_t dy_addr = smem_base + (uint32_t)st * p.stage_bytes;
-                for (int ti = 0; ti < nt; ++ti) {
+                // One M=128 MMA reads 128/CB consecutive X boxes: with Cin <= 64 these are the boxes of R consecutive
+                // taps (rows = (tap, channel)), so ONE accumulator serves R taps and the MMA count drops R-fold.
+                for (int ti = 0; ti < nt; ti += p.R) {
                     const uint32_t x_addr = dy_addr + dy_region + (uint32_t)ti * x_region;
-                    const uint32_t d_tmem = tmem + (uint32_t)(ti * p.BN);
+                    const uint32_t d_tmem = tmem + (uint32_t)((ti / p.R) * p.BN);
 #pragma unroll
                     for (int kk = 0; kk < KP / 16; ++kk) {
                         const uint64_t da = umma_smem_desc(x_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
@@ -137,13 +139,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         }
     } else {
         const int q = warp & 3;
-        const int ci = ci0 + q * 32 + lane;
-        const bool valid = ci < p.Cin;
+        const int row = q * 32 + lane;
+        const int rows_per_tap = p.n_a_max * CB;          // accumulator rows that belong to one tap
+        const int t_in_group = row / rows_per_tap;        // 0 unless R > 1
+        const int ci = ci0 + row - t_in_group * rows_per_tap;
         mbar_wait(tfull, 0);
         tc_fence_after();
-        for (int ti = 0; ti < nt; ++ti) {
-            float* orow = p.dw_out + p.dw_off + (long long)p.tap_flat[tap0 + ti] * p.dw_stap + (long long)ci * p.dw_sci + co0;
-            const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ti * p.BN);
+        for (int ti = 0; ti < nt; ti += p.R) {
+            const int tap_i = ti + t_in_group;
+            const bool valid = (t_in_group < p.R) && (tap_i < nt) && (ci < p.Cin);
+            float* orow = p.dw_out + p.dw_off + (long long)p.tap_flat[tap0 + (valid ? tap_i : ti)] * p.dw_stap + (long long)ci * p.dw_sci + co0;
+            const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((ti / p.R) * p.BN);
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
                 float v[16];
                 __syncwarp();
@@ -207,7 +213,10 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     p.n_a_max = ((d->Cin < 128 ? d->Cin : 128) + CB - 1) / CB;
     p.n_b_max = (p.BN + CB - 1) / CB;
     // taps per CTA: limited by TMEM (T accumulators of BN columns) and by shared memory (<= 11 boxes = 88 KB per stage)
-    int t_max = 512 / p.BN;
+    p.R = (128 / CB) / p.n_a_max;            // taps per M=128 MMA
+    if (p.R < 1) p.R = 1;
+    if (const char* e = getenv("KP_WGRAD_TAPS_PER_MMA")) { const int c = atoi(e); if (c >= 1 && c < p.R) p.R = c; }
+    int t_max = (512 / p.BN) * p.R;
     const size_t slack = (size_t)(128 / CB - p.n_a_max) * p.box_bytes;
     int boxes_per_stage = (int)(((215u * 1024u - slack) / 2) / p.box_bytes);   // two stages must fit ...
     if (boxes_per_stage > 8) boxes_per_stage = 8;   // ... but 3-4 stages hide the TMA latency much better (<= 64 KB per stage)
@@ -219,7 +228,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     const int groups = (d->n_taps + t_max - 1) / t_max;
     p.T = (d->n_taps + groups - 1) / groups;
     int tm = 32;
-    while (tm < p.T * p.BN) tm <<= 1;
+    while (tm < ((p.T + p.R - 1) / p.R) * p.BN) tm <<= 1;
     p.tmem_cols = tm;
     p.stage_bytes = (uint32_t)(p.T * p.n_a_max + p.n_b_max) * p.box_bytes;
     int stages = (int)((215u * 1024u - slack) / p.stage_bytes);
