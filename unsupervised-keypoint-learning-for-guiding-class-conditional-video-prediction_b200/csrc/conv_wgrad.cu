@@ -31,7 +31,7 @@ struct alignas(64) WgradKParams {
     int n_taps, T, R;                    // taps per CTA (group size); taps covered by ONE M=128 MMA (R > 1 when Cin <= 64)
     int Cin, Cout, BN, co_blocks, tmem_cols, stages;
     int n_a_max, n_b_max;
-    uint32_t box_bytes, stage_bytes;
+    uint32_t box_bytes, ybox_bytes, stage_bytes;
     float* dw_out;
     long long dw_off, dw_stap, dw_sci;
 };
@@ -40,12 +40,19 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int CB>
+// CB = channel block of the X operand (rows of dW), CBY = channel block of the dY operand (columns of dW): each follows
+// its own channel count (64 if divisible by 64, else 32, else 16), so a 64->8 layer moves X in 128-byte rows even
+// though dY only has 16-byte... 32-byte rows.  Pixels per stage follow X (its boxes are 8 KB).
+template <int CB, int CBY>
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
     constexpr uint32_t ROW_BYTES = CB * 2;
     constexpr uint32_t SBO = 8 * ROW_BYTES;
     constexpr uint32_t LAYOUT = (CB == 64) ? 2u : (CB == 32) ? 4u : 6u;
     constexpr uint32_t KSTEP_BYTES = 16 * ROW_BYTES;  // 16 pixels per UMMA K-step
+    constexpr uint32_t ROW_BYTES_Y = CBY * 2;
+    constexpr uint32_t SBO_Y = 8 * ROW_BYTES_Y;
+    constexpr uint32_t LAYOUT_Y = (CBY == 64) ? 2u : (CBY == 32) ? 4u : 6u;
+    constexpr uint32_t KSTEP_BYTES_Y = 16 * ROW_BYTES_Y;
     constexpr int KP = 4096 / CB;                     // pixels per stage
 
     extern __shared__ uint8_t smem_dyn[];
@@ -67,10 +74,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     const int n_iters = t_end - t_begin;  // host guarantees >= 1
 
     const int n_a = min(128 / CB, (p.Cin - ci0 + CB - 1) / CB);
-    const int n_b = (min(p.BN, p.Cout - co0) + CB - 1) / CB;
+    const int n_b = (min(p.BN, p.Cout - co0) + CBY - 1) / CBY;
     // stage layout: [dY: n_b_max boxes][X of tap 0: n_a_max boxes][X of tap 1] ...
     const uint32_t x_region = (uint32_t)p.n_a_max * p.box_bytes;
-    const uint32_t dy_region = (uint32_t)p.n_b_max * p.box_bytes;
+    const uint32_t dy_region = (uint32_t)p.n_b_max * p.ybox_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
             tma_prefetch_desc(&p.mapDY);
             for (int m = 0; m < KP_MAX_MAPS; ++m)
                 if (m == 0 || p.mf[tap0] == m) tma_prefetch_desc(&p.mapX[m]);
-            const uint32_t tx = (uint32_t)(nt * n_a + n_b) * p.box_bytes;
+            const uint32_t tx = (uint32_t)(nt * n_a) * p.box_bytes + (uint32_t)n_b * p.ybox_bytes;
             for (int it = 0; it < n_iters; ++it) {
                 const int tile = t_begin + it;
                 const int w0 = (tile % p.tiles_w) * p.TW;
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                 uint8_t* dy_dst = base + (size_t)st * p.stage_bytes;
                 mbar_arrive_expect_tx(&full[st], tx);
                 for (int c = 0; c < n_b; ++c)
-                    tma_load_4d(dy_dst + (size_t)c * p.box_bytes, &p.mapDY, &full[st], co0 + c * CB, w0, h0, n0);
+                    tma_load_4d(dy_dst + (size_t)c * p.ybox_bytes, &p.mapDY, &full[st], co0 + c * CBY, w0, h0, n0);
                 for (int ti = 0; ti < nt; ++ti) {
                     const int t = tap0 + ti;
                     uint8_t* x_dst = dy_dst + dy_region + (size_t)ti * x_region;
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 #pragma unroll
                     for (int kk = 0; kk < KP / 16; ++kk) {
                         const uint64_t da = umma_smem_desc(x_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
-                        const uint64_t db = umma_smem_desc(dy_addr + kk * KSTEP_BYTES, SBO, p.box_bytes, LAYOUT);
+                        const uint64_t db = umma_smem_desc(dy_addr + kk * KSTEP_BYTES_Y, SBO_Y, p.ybox_bytes, LAYOUT_Y);
                         umma_bf16_if(leader, d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
                     }
                 }
@@ -183,14 +190,16 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     KP_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cin > 0 && d->Cout > 0, "kp_wgrad: empty problem");
     WgradKParams p;
     memset(&p, 0, sizeof(p));
-    const int CB = d->CB;
+    // operand channel blocks follow the operands' own channel counts (desc->CB is only validated)
+    auto blk = [](int c) { return c % 64 == 0 ? 64 : c % 32 == 0 ? 32 : 16; };
+    const int CB = blk(d->Cin), CBY = blk(d->Cout);
     choose_pixel_tile(wg_kp(CB), d->Wo, d->Ho, d->N, &p.TW, &p.TH, &p.TN);
     for (int m = 0; m < d->n_maps; ++m) {
         const int rc = encode_view_map(&p.mapX[m], d->map[m], x, d->N, CB, p.TW, p.TH, p.TN, "kp_wgrad X map");
         if (rc != KP_OK) return rc;
     }
     {
-        const int rc = encode_view_map(&p.mapDY, d->dy, dy, d->N, CB, p.TW, p.TH, p.TN, "kp_wgrad dY map");
+        const int rc = encode_view_map(&p.mapDY, d->dy, dy, d->N, CBY, p.TW, p.TH, p.TN, "kp_wgrad dY map");
         if (rc != KP_OK) return rc;
     }
     for (int t = 0; t < d->n_taps; ++t) {
@@ -207,20 +216,22 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     p.co_blocks = (cout_pad + p.BN - 1) / p.BN;
     const int ci_blocks = (d->Cin + 127) / 128;
     p.box_bytes = (uint32_t)wg_kp(CB) * CB * 2u;                          // 8 KB
+    p.ybox_bytes = (uint32_t)wg_kp(CB) * CBY * 2u;                        // 2-32 KB (same pixels, dY's block)
     // X regions hold only the channel chunks that exist (the MMA still reads 128 rows = 128/CB chunks at LBO stride:
     // rows past the loaded chunks alias the next tap's region / the next stage / the slack below and only produce
     // accumulator rows that are never stored)
     p.n_a_max = ((d->Cin < 128 ? d->Cin : 128) + CB - 1) / CB;
-    p.n_b_max = (p.BN + CB - 1) / CB;
+    p.n_b_max = (p.BN + CBY - 1) / CBY;
     // taps per CTA: limited by TMEM (T accumulators of BN columns) and by shared memory (<= 11 boxes = 88 KB per stage)
     p.R = (128 / CB) / p.n_a_max;            // taps per M=128 MMA
     if (p.R < 1) p.R = 1;
     if (const char* e = getenv("KP_WGRAD_TAPS_PER_MMA")) { const int c = atoi(e); if (c >= 1 && c < p.R) p.R = c; }
     int t_max = (512 / p.BN) * p.R;
     const size_t slack = (size_t)(128 / CB - p.n_a_max) * p.box_bytes;
-    int boxes_per_stage = (int)(((215u * 1024u - slack) / 2) / p.box_bytes);   // two stages must fit ...
-    if (boxes_per_stage > 8) boxes_per_stage = 8;   // ... but 3-4 stages hide the TMA latency much better (<= 64 KB per stage)
-    const int by_smem = (boxes_per_stage - p.n_b_max) / p.n_a_max;
+    const uint32_t dy_bytes = (uint32_t)p.n_b_max * p.ybox_bytes;
+    uint32_t stage_cap = (uint32_t)((215u * 1024u - slack) / 2);               // two stages must fit ...
+    if (stage_cap > 64u * 1024u) stage_cap = 64u * 1024u;   // ... but 3-4 stages hide the TMA latency much better
+    const int by_smem = stage_cap > dy_bytes ? (int)((stage_cap - dy_bytes) / ((uint32_t)p.n_a_max * p.box_bytes)) : 0;
     if (t_max > by_smem) t_max = by_smem;
     if (t_max > d->n_taps) t_max = d->n_taps;
     if (const char* e = getenv("KP_WGRAD_TMAX")) { const int c = atoi(e); if (c >= 1 && c < t_max) t_max = c; }
@@ -230,7 +241,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     int tm = 32;
     while (tm < ((p.T + p.R - 1) / p.R) * p.BN) tm <<= 1;
     p.tmem_cols = tm;
-    p.stage_bytes = (uint32_t)(p.T * p.n_a_max + p.n_b_max) * p.box_bytes;
+    p.stage_bytes = ((uint32_t)(p.T * p.n_a_max) * p.box_bytes + dy_bytes + 1023u) & ~1023u;
     int stages = (int)((215u * 1024u - slack) / p.stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
@@ -255,19 +266,26 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024 + slack;
     KP_REQUIRE(smem <= 227u * 1024u, "kp_wgrad: shared memory %zu exceeds the SM (internal tiling error)", smem);
     dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)groups, (unsigned)splits);
-#define KP_LAUNCH_WGRAD(CBV)                                                                                     \
-    do {                                                                                                         \
-        static bool attr_done = false;                                                                           \
-        if (!attr_done) {                                                                                        \
-            KP_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                               227 * 1024));                                                     \
-            attr_done = true;                                                                                    \
-        }                                                                                                        \
-        wgrad_kernel<CBV><<<grid, 192, smem, st>>>(p);                                                           \
+#define KP_LAUNCH_WGRAD(CBX, CBYV)                                                                                  \
+    do {                                                                                                            \
+        static bool attr_done = false;                                                                              \
+        if (!attr_done) {                                                                                           \
+            KP_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel<CBX, CBYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               227 * 1024));                                                        \
+            attr_done = true;                                                                                       \
+        }                                                                                                           \
+        wgrad_kernel<CBX, CBYV><<<grid, 192, smem, st>>>(p);                                                        \
     } while (0)
-    if (CB == 64) KP_LAUNCH_WGRAD(64);
-    else if (CB == 32) KP_LAUNCH_WGRAD(32);
-    else KP_LAUNCH_WGRAD(16);
+#define KP_LAUNCH_WGRAD_Y(CBX)                         \
+    do {                                               \
+        if (CBY == 64) KP_LAUNCH_WGRAD(CBX, 64);       \
+        else if (CBY == 32) KP_LAUNCH_WGRAD(CBX, 32);  \
+        else KP_LAUNCH_WGRAD(CBX, 16);                 \
+    } while (0)
+    if (CB == 64) KP_LAUNCH_WGRAD_Y(64);
+    else if (CB == 32) KP_LAUNCH_WGRAD_Y(32);
+    else KP_LAUNCH_WGRAD_Y(16);
+#undef KP_LAUNCH_WGRAD_Y
 #undef KP_LAUNCH_WGRAD
     KP_LAUNCHED();
     return KP_OK;
