@@ -44,6 +44,7 @@ struct alignas(64) HaloKParams {
     int R, pitch;
     uint32_t plane_bytes, a_slot_bytes, b_bytes, b_stage_bytes, pitch_rcp;
     int NSA, NSB, halves, acc_bufs;
+    int gather_depth;
     int TB, tap_groups, resident;      // taps per weight stage, stages per slot; resident: all weights loaded once
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int Ho, Wo, N, BN, tmem_cols;
@@ -62,6 +63,13 @@ __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// wait until at most `n` (0..3) of this thread's most recent cp.async groups are still in flight
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    if (n <= 0) cp_async_wait<0>();
+    else if (n == 1) cp_async_wait<1>();
+    else if (n == 2) cp_async_wait<2>();
+    else cp_async_wait<3>();
+}
 
 template <int HALVES>
 __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_constant__ HaloKParams p) {
@@ -113,14 +121,31 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
         const int tid = threadIdx.x;
         const int halo_px = p.R * p.pitch;
         uint32_t ga = 0;
-        int prev_st = -1;
+        // `depth` slots are in flight per thread, signalled in issue order, oldest first.  Measured: depth 2-3 does not
+        // help the small-channel layers (the gather is not their bottleneck) and costs 64-channel slots 15-40 %
+        // (more cp.async in flight than the LSU queue absorbs), so the default is 1.
+        const int depth = min(p.gather_depth, p.NSA - 1);
+        int pending = 0;
         for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x) {
             const int mt = work / p.n_tiles;
             const int n = mt / tiles_per_image, r = mt - n * tiles_per_image;
             const int y0 = (r / p.tiles_w) * tile_rows + p.dh_min, x0 = (r % p.tiles_w) * 8 + p.dw_min;
             for (int s = 0; s < p.n_slots; ++s, ++ga) {
                 const int st = (int)(ga % (uint32_t)p.NSA);
-                if (ga >= (uint32_t)p.NSA) mbar_wait(&emptyA[st], ((ga / (uint32_t)p.NSA) - 1) & 1);
+                if (ga >= (uint32_t)p.NSA) {
+                    const uint32_t par = ((ga / (uint32_t)p.NSA) - 1) & 1;
+                    if (!mbar_try_wait(&emptyA[st], par)) {
+                        // ring full: the MMA warp is the slow side.  Hand over everything still in flight before
+                        // blocking, otherwise the consumer would wait for slots that have long landed.
+                        while (pending > 0) {
+                            cp_async_wait_dyn(pending - 1);
+                            fence_proxy_async_smem();
+                            mbar_arrive(&fullA[(int)((ga - (uint32_t)pending) % (uint32_t)p.NSA)]);
+                            --pending;
+                        }
+                        mbar_wait(&emptyA[st], par);
+                    }
+                }
                 const int m = p.sl_src[s], nch = p.sl_nch[s];
                 const int nj = nch >> 3;                       // 16-byte chunks per pixel: 1, 2, 4 or 8
                 const int j = tid & (nj - 1);
@@ -144,18 +169,20 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(z0 + (uint32_t)px * 16u), "r"(0u) : "memory");
                 }
                 cp_async_commit();
-                if (prev_st >= 0) {
-                    cp_async_wait<1>();           // the previous slot has landed (this one is still in flight)
+                ++pending;
+                if (pending > depth) {
+                    cp_async_wait_dyn(depth);     // the oldest slot in flight has landed
                     fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core's async proxy
-                    mbar_arrive(&fullA[prev_st]);
+                    mbar_arrive(&fullA[(int)((ga + 1u - (uint32_t)pending) % (uint32_t)p.NSA)]);
+                    --pending;
                 }
-                prev_st = st;
             }
         }
-        if (prev_st >= 0) {
-            cp_async_wait<0>();
+        while (pending > 0) {
+            cp_async_wait_dyn(pending - 1);
             fence_proxy_async_smem();
-            mbar_arrive(&fullA[prev_st]);
+            mbar_arrive(&fullA[(int)((ga - (uint32_t)pending) % (uint32_t)p.NSA)]);
+            --pending;
         }
     } else if (warp == 4) {
         // ------------------------------- weight TMA -------------------------------
@@ -419,6 +446,8 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     for (int s = 0; s < ns; ++s) max_planes = p.sl_nch[s] / 8 > max_planes ? p.sl_nch[s] / 8 : max_planes;
     p.a_slot_bytes = ((uint32_t)max_planes * p.plane_bytes + 127u) & ~127u;
     p.b_bytes = (uint32_t)BN * 128u;
+    p.gather_depth = 1;
+    if (const char* e = getenv("KP_HALO_GATHER_DEPTH")) { const int c = atoi(e); if (c >= 1 && c <= 3) p.gather_depth = c; }
     p.pitch_rcp = (65536u + (uint32_t)p.pitch - 1u) / (uint32_t)p.pitch;
     for (int m = 0; m < d->n_maps; ++m)
         KP_REQUIRE((long long)p.s_H[m] * p.s_sh[m] + (long long)p.s_W[m] * p.s_sw[m] < (1ll << 31),
