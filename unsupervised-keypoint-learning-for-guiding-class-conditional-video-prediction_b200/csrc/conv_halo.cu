@@ -110,11 +110,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 5) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
+    pdl_wait();
 
     if (warp < 4) {
         // ------------------------------- activation gather (cp.async) -------------------------------
@@ -519,8 +521,8 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
         KP_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    if (p.halves == 2) haloconv_kernel<2><<<grid, HALO_THREADS, smem, st>>>(p);
-    else haloconv_kernel<1><<<grid, HALO_THREADS, smem, st>>>(p);
+    if (p.halves == 2) KP_CUDA_CHECK(launch_pdl(haloconv_kernel<2>, dim3(grid), dim3(HALO_THREADS), smem, st, p));
+    else KP_CUDA_CHECK(launch_pdl(haloconv_kernel<1>, dim3(grid), dim3(HALO_THREADS), smem, st, p));
     KP_LAUNCHED();
     return KP_OK;
 }

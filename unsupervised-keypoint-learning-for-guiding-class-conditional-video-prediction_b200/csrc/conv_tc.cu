@@ -92,11 +92,13 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 1) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
+    pdl_wait();      // everything above overlaps the tail of the previous kernel; global memory is touched below only
 
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
@@ -249,6 +251,15 @@ static EncodeTiledFn get_encode_fn() {
 
 static CUtensorMapSwizzle swizzle_for(int CB) {
     return CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("KP_PDL");
+        on = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    }
+    return on == 1;
 }
 
 int device_sm_count() {
@@ -449,7 +460,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
                                                227 * 1024));                                                        \
             attr_done = true;                                                                                       \
         }                                                                                                           \
-        tapconv_kernel<CBV><<<grid, 192, smem, st>>>(p);                                                            \
+        KP_CUDA_CHECK(launch_pdl(tapconv_kernel<CBV>, dim3(grid), dim3(192), smem, st, p));                                                            \
     } while (0)
     if (CB == 64) KP_LAUNCH_TAPCONV(64);
     else if (CB == 32) KP_LAUNCH_TAPCONV(32);

@@ -87,11 +87,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         mbar_init(tfull, 1);
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     if (warp == 1) tmem_alloc(tslot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -274,7 +276,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
                                                227 * 1024));                                                        \
             attr_done = true;                                                                                       \
         }                                                                                                           \
-        wgrad_kernel<CBX, CBYV><<<grid, 192, smem, st>>>(p);                                                        \
+        KP_CUDA_CHECK(launch_pdl(wgrad_kernel<CBX, CBYV>, grid, dim3(192), smem, st, p));                            \
     } while (0)
 #define KP_LAUNCH_WGRAD_Y(CBX)                         \
     do {                                               \

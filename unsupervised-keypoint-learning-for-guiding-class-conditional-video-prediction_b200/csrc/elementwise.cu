@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                     const BnFin fin, int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ out) {
     extern __shared__ float sp[];   // [2][C]
+    pdl_launch_dependents();
+    pdl_wait();
     if (fin.ssum != nullptr) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             const double m0 = (double)fin.ssum[c] / fin.count;
@@ -258,6 +260,8 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ rstd, int relu, int N, int H, int W, int C, float* __restrict__ dbeta,
                          float* __restrict__ dgamma) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int CG = C >> 3;                 // power of two, <= 256
     const int cg = threadIdx.x % CG;
     const int lanes = blockDim.x / CG;     // pixel lanes per block
@@ -342,6 +346,8 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloa
                         int relu, int N, int H, int W, int C, __nv_bfloat16* __restrict__ dx,
                         float* __restrict__ gbeta_acc, float* __restrict__ ggamma_acc) {
     extern __shared__ float sp[];   // [4][C]: sc, sh, k1, k0
+    pdl_launch_dependents();
+    pdl_wait();
     if (blockIdx.x == 0 && gbeta_acc != nullptr) {
         // fold this call's dbeta / dgamma into the parameter-gradient buffers (the shared pose_encoder accumulates two calls)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -663,17 +669,23 @@ channel_sum_kernel(const __nv_bfloat16* __restrict__ g, long long P, int C, floa
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] += t[j];
     }
-    __shared__ float red[256 * 8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = s[j];
+    // tree reduction (shuffles when the channel groups tile a warp, shared-memory atomics across warps, one global atomic
+    // per channel per block) - the serial walk by pixel lane 0 cost 36 us per call for C = 8
+    __shared__ float red[2048];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
-    if (pl == 0) {
-        for (int l = 1; l < lanes; ++l)
+    const bool tiled = CG < 32 && (CG & (CG - 1)) == 0;
+    if (tiled) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] += red[(l * CG + cg) * 8 + j];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(out + cg * 8 + j, s[j]);
+        for (int j = 0; j < 8; ++j)
+            for (int off = 16; off >= CG; off >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
     }
+    if (pl < lanes && (!tiled || (threadIdx.x & 31) < CG)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&red[cg * 8 + j], s[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, red[c]);
 }
 
 // =============================================================================================
@@ -711,8 +723,8 @@ static int bn_apply_launch(const void* x, const float* scale, const float* shift
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     const size_t smem = 2 * (size_t)C * sizeof(float);
-    if (upsample) bn_act_apply_kernel<true><<<grid_for(total, 256), 256, smem, st>>>(xi, scale, shift, fin, relu, N, H, W, C, o);
-    else bn_act_apply_kernel<false><<<grid_for((total + 1) / 2, 256), 256, smem, st>>>(xi, scale, shift, fin, relu, N, H, W, C, o);
+    if (upsample) KP_CUDA_CHECK(launch_pdl(bn_act_apply_kernel<true>, dim3(grid_for(total, 256)), dim3(256), smem, st, xi, scale, shift, fin, relu, N, H, W, C, o));
+    else KP_CUDA_CHECK(launch_pdl(bn_act_apply_kernel<false>, dim3(grid_for((total + 1) / 2, 256)), dim3(256), smem, st, xi, scale, shift, fin, relu, N, H, W, C, o));
     KP_LAUNCHED();
     return KP_OK;
 }
@@ -742,16 +754,16 @@ int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const flo
     const int lanes = 256 / (C / 8);
     const int rgrid = grid_for((P + 2 * lanes - 1) / (2 * lanes), 1, 148 * 6);
     if (upsample)
-        bn_act_bwd_reduce_kernel<true><<<rgrid, 256, 0, st>>>(d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma);
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_reduce_kernel<true>, dim3(rgrid), dim3(256), 0, st, d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma));
     else
-        bn_act_bwd_reduce_kernel<false><<<rgrid, 256, 0, st>>>(d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma);
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_reduce_kernel<false>, dim3(rgrid), dim3(256), 0, st, d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma));
     KP_LAUNCHED();
     const long long total = P * (C / 8);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dx);
     if (upsample)
-        bn_act_bwd_apply_kernel<true><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc);
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_apply_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 4 * (size_t)C * sizeof(float), st, d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc));
     else
-        bn_act_bwd_apply_kernel<false><<<grid_for(total, 256), 256, 4 * (size_t)C * sizeof(float), st>>>(d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc);
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_apply_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 4 * (size_t)C * sizeof(float), st, d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc));
     KP_LAUNCHED();
     return KP_OK;
 }

@@ -121,6 +121,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still draining; `pdl_wait` blocks until the predecessor grid has completed and
+// its memory is visible (every global access of the kernel must come after it), `pdl_launch_dependents` tells the
+// scheduler that the NEXT kernel may be started as soon as resources free up.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }

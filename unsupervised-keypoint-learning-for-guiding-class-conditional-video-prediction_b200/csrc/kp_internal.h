@@ -20,6 +20,24 @@ int k1_render_colorize(const float* mu, const float* colors, int B, int K, int h
 int k1_colorize(const float* maps, const float* colors, long long P, int K, float* out, cudaStream_t st);
 
 // conv_tc.cu
+// Launch with the PDL attribute when KP_PDL=1 (see kp_common.cuh; the kernel must call pdl_wait() before its first global
+// access).  Inside a stream capture this becomes a programmatic dependency edge of the CUDA graph.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 bool haloconv_eligible(const kp_tapconv_desc* d, const float* ssum);
 int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
                     float* ssum, float* ssq, cudaStream_t st);
