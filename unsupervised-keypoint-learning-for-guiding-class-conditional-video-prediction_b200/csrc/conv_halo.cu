@@ -22,6 +22,7 @@
 #include "kp_internal.h"
 #include <cudaTypedefs.h>
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace kp {
@@ -45,6 +46,8 @@ struct alignas(64) HaloKParams {
     uint32_t plane_bytes, a_slot_bytes, b_bytes, b_stage_bytes, pitch_rcp;
     int NSA, NSB, halves, acc_bufs;
     int gather_depth;
+    uint32_t rcp_ntiles, rcp_tpi, rcp_tw;            // ceil(2^32/d): exact x/d for x*d < 2^32 (work decode without divisions)
+    unsigned short tapoff[KP_MAX_TAPS];              // dh*pitch + dw of each tap (16-byte units inside the halo)
     int TB, tap_groups, resident;      // taps per weight stage, stages per slot; resident: all weights loaded once
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int Ho, Wo, N, BN, tmem_cols;
@@ -55,7 +58,18 @@ struct alignas(64) HaloKParams {
     const float* bias;
     float* ssum;
     float* ssq;
+    unsigned long long* dbg;   // KP_TAPCONV_TRACE: per-item timestamps of CTA 0 (debug only)
 };
+
+__device__ __forceinline__ unsigned long long halo_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KP_HTRACE(slot, idx)                                                                            \
+    do {                                                                                                \
+        if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 24) p.dbg[(idx) * 8 + (slot)] = halo_gtime(); \
+    } while (0)
 
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -70,6 +84,8 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
     else if (n == 2) cp_async_wait<2>();
     else cp_async_wait<3>();
 }
+
+__device__ __forceinline__ int fdiv(int x, uint32_t rcp) { return rcp == 0u ? x : (int)__umulhi((uint32_t)x, rcp); }   // rcp 0 = divide by 1
 
 template <int HALVES>
 __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_constant__ HaloKParams p) {
@@ -128,10 +144,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
         // (more cp.async in flight than the LSU queue absorbs), so the default is 1.
         const int depth = min(p.gather_depth, p.NSA - 1);
         int pending = 0;
-        for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x) {
-            const int mt = work / p.n_tiles;
-            const int n = mt / tiles_per_image, r = mt - n * tiles_per_image;
-            const int y0 = (r / p.tiles_w) * tile_rows + p.dh_min, x0 = (r % p.tiles_w) * 8 + p.dw_min;
+        int ltg = 0;
+        for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x, ++ltg) {
+            const int mt = fdiv(work, p.rcp_ntiles);
+            const int n = fdiv(mt, p.rcp_tpi), r = mt - n * tiles_per_image;
+            const int tr = fdiv(r, p.rcp_tw);
+            const int y0 = tr * tile_rows + p.dh_min, x0 = (r - tr * p.tiles_w) * 8 + p.dw_min;
             for (int s = 0; s < p.n_slots; ++s, ++ga) {
                 const int st = (int)(ga % (uint32_t)p.NSA);
                 if (ga >= (uint32_t)p.NSA) {
@@ -148,10 +166,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                         mbar_wait(&emptyA[st], par);
                     }
                 }
-                const int m = p.sl_src[s], nch = p.sl_nch[s];
+                if (tid == 0 && s == 0) KP_HTRACE(0, ltg);
+                // (with one slot per item - every small-channel layer - s is always 0 and these loads are loop invariant)
+                const int sq = p.n_slots == 1 ? 0 : s;
+                const int m = p.sl_src[sq], nch = p.sl_nch[sq];
                 const int nj = nch >> 3;                       // 16-byte chunks per pixel: 1, 2, 4 or 8
                 const int j = tid & (nj - 1);
-                const __nv_bfloat16* sbase = p.src[m] + (long long)n * p.s_sn[m] + p.sl_c0[s] + 8 * j;
+                const __nv_bfloat16* sbase = p.src[m] + (long long)n * p.s_sn[m] + p.sl_c0[sq] + 8 * j;
                 const uint32_t dst0 = a_base + (uint32_t)st * p.a_slot_bytes + (uint32_t)j * p.plane_bytes;
                 const int H = p.s_H[m], W = p.s_W[m];
                 const int sh = (int)p.s_sh[m], sw = (int)p.s_sw[m];    // per-image offsets fit 32 bits (host checks)
@@ -171,6 +192,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(z0 + (uint32_t)px * 16u), "r"(0u) : "memory");
                 }
                 cp_async_commit();
+                if (tid == 0 && s == p.n_slots - 1) KP_HTRACE(1, ltg);
                 ++pending;
                 if (pending > depth) {
                     cp_async_wait_dyn(depth);     // the oldest slot in flight has landed
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
             } else {
                 uint32_t gb = 0;
                 for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x) {
-                    const int n_off = (work % p.n_tiles) * p.BN;
+                    const int n_off = (work - fdiv(work, p.rcp_ntiles) * p.n_tiles) * p.BN;
                     for (int s = 0; s < p.n_slots; ++s) {
                         for (int t0 = 0; t0 < p.n_taps; t0 += p.TB, ++gb) {
                             const int nt = min(p.TB, p.n_taps - t0);
@@ -238,12 +260,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                 const int acc = acc_bufs == 2 ? (lt & 1) : 0;
                 if (lt >= acc_bufs) mbar_wait(&tempty[acc], ((lt / acc_bufs) - 1) & 1);
                 tc_fence_after();
+                if (lane == 0) KP_HTRACE(2, lt);
                 const uint32_t d0 = tmem + (uint32_t)acc * (uint32_t)HALVES * BN;
                 uint32_t accum = 0;
                 for (int s = 0; s < n_slots; ++s, ++ga) {
                     const int stA = (int)(ga % (uint32_t)NSA);
                     mbar_wait(&fullA[stA], (ga / (uint32_t)NSA) & 1);
                     tc_fence_after();
+                    if (lane == 0 && s == n_slots - 1) KP_HTRACE(3, lt);
                     const uint32_t a16 = (a_base + (uint32_t)stA * p.a_slot_bytes) >> 4;
                     const int ksteps = (p.sl_nch[s] + 15) >> 4;
                     for (int t0 = 0; t0 < n_taps; t0 += TB) {
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                         }
                         const int t1 = min(t0 + TB, n_taps);
                         for (int t = t0; t < t1; ++t, b16 += b_box16) {
-                            const uint32_t at16 = a16 + (uint32_t)p.dh[t] * (uint32_t)p.pitch + (uint32_t)p.dw[t];
+                            const uint32_t at16 = a16 + (uint32_t)p.tapoff[t];
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
                                 if (kk < ksteps) {
@@ -283,6 +307,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                     }
                     umma_commit_if(leader, &emptyA[stA]);
                 }
+                if (lane == 0) KP_HTRACE(4, lt);
                 umma_commit_if(leader, &tfull[acc]);
             }
         }
@@ -299,13 +324,15 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
         named_bar_sync(1, 128);
         int lt = 0;
         for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x, ++lt) {
-            const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
-            const int n = mt / tiles_per_image, r = mt - n * tiles_per_image;
-            const int h0 = (r / p.tiles_w) * tile_rows, w0 = (r % p.tiles_w) * 8;
+            const int mt = fdiv(work, p.rcp_ntiles), nt = work - mt * p.n_tiles;
+            const int n = fdiv(mt, p.rcp_tpi), r = mt - n * tiles_per_image;
+            const int tr = fdiv(r, p.rcp_tw);
+            const int h0 = tr * tile_rows, w0 = (r - tr * p.tiles_w) * 8;
             const int n_off = nt * p.BN;
             const int acc = p.acc_bufs == 2 ? (lt & 1) : 0;
             mbar_wait(&tfull[acc], (lt / p.acc_bufs) & 1);
             tc_fence_after();
+            if (et == 0) KP_HTRACE(5, lt);
             for (int hf = 0; hf < HALVES; ++hf) {
                 const int uh = h0 + hf * 16 + th, uw = w0 + tw;
                 const bool valid = (uh < p.Ho) && (uw < p.Wo);
@@ -328,6 +355,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
                     epi_chunk(p, v, n_off + c0, valid, pix, lane, 0, s_bias, s_stat);
                 }
             }
+            if (et == 0) KP_HTRACE(6, lt);
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
@@ -450,6 +478,7 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     p.b_bytes = (uint32_t)BN * 128u;
     p.gather_depth = 1;
     if (const char* e = getenv("KP_HALO_GATHER_DEPTH")) { const int c = atoi(e); if (c >= 1 && c <= 3) p.gather_depth = c; }
+    auto rcp32 = [](int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); };
     p.pitch_rcp = (65536u + (uint32_t)p.pitch - 1u) / (uint32_t)p.pitch;
     for (int m = 0; m < d->n_maps; ++m)
         KP_REQUIRE((long long)p.s_H[m] * p.s_sh[m] + (long long)p.s_W[m] * p.s_sw[m] < (1ll << 31),
@@ -503,6 +532,10 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     p.tiles_w = (d->Wo + 7) / 8;
     p.tiles_h = (d->Ho + 16 * p.halves - 1) / (16 * p.halves);
     p.total_tiles = d->N * p.tiles_w * p.tiles_h * p.n_tiles;
+    p.rcp_ntiles = rcp32(p.n_tiles); p.rcp_tpi = rcp32(p.tiles_w * p.tiles_h); p.rcp_tw = rcp32(p.tiles_w);
+    KP_REQUIRE((long long)p.total_tiles * (p.tiles_w * p.tiles_h > p.n_tiles ? p.tiles_w * p.tiles_h : p.n_tiles) < (1ll << 32),
+               "kp_tapconv(halo): too many tiles for the 32-bit work decode");
+    for (int t = 0; t < d->n_taps; ++t) p.tapoff[t] = (unsigned short)(p.dh[t] * p.pitch + p.dw[t]);
     p.Ho = d->Ho; p.Wo = d->Wo; p.N = d->N;
     p.out = out;
     p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
@@ -515,6 +548,12 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     KP_REQUIRE(smem <= 227u * 1024u, "kp_tapconv(halo): shared memory %zu exceeds the SM", smem);
     int grid = device_sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
+    unsigned long long* trace = nullptr;
+    if (getenv("KP_TAPCONV_TRACE")) {
+        cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
+        cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
+    }
+    p.dbg = trace;
     static bool attr_done = false;
     if (!attr_done) {
         KP_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -524,6 +563,22 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     if (p.halves == 2) KP_CUDA_CHECK(launch_pdl(haloconv_kernel<2>, dim3(grid), dim3(HALO_THREADS), smem, st, p));
     else KP_CUDA_CHECK(launch_pdl(haloconv_kernel<1>, dim3(grid), dim3(HALO_THREADS), smem, st, p));
     KP_LAUNCHED();
+    if (trace != nullptr) {
+        unsigned long long h[24 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 24 * 8; ++i) if (h[i] != 0 && h[i] < t0) t0 = h[i];
+        fprintf(stderr, "haloconv trace grid=%d halves=%d slots=%d taps=%d BN=%d NSA=%d NSB=%d resident=%d items=%d: item: gather_start gather_issued "
+                "mma_start mma_data mma_issued epi_go epi_done (ns)\n", grid, p.halves, p.n_slots, p.n_taps, p.BN, p.NSA, p.NSB, p.resident, p.total_tiles);
+        for (int t = 0; t < 24; ++t) {
+            if (h[t * 8] == 0) break;
+            fprintf(stderr, "  %2d:", t);
+            for (int k = 0; k < 7; ++k) fprintf(stderr, " %7lld", h[t * 8 + k] ? (long long)(h[t * 8 + k] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(trace);
+    }
     return KP_OK;
 }
 

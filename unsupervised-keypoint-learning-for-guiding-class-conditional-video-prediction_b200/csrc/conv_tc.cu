@@ -21,6 +21,7 @@
 #include "kp_internal.h"
 #include <cudaTypedefs.h>
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace kp {
@@ -43,7 +44,18 @@ struct alignas(64) TapConvKParams {
     const float* bias;
     float* ssum;
     float* ssq;
+    unsigned long long* dbg;   // KP_TAPCONV_TRACE: per-tile timestamps of CTA 0 (debug only)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KP_TRACE(slot, tileidx)                                                                   \
+    do {                                                                                          \
+        if (p.dbg != nullptr && blockIdx.x == 0 && (tileidx) < 24) p.dbg[(tileidx) * 8 + (slot)] = gtime(); \
+    } while (0)
 
 __device__ __forceinline__ float apply_act(float x, int act, float alpha, bool last) {
     switch (act) {
@@ -107,8 +119,10 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 if (p.nblk[m] > 0) tma_prefetch_desc(&p.mapA[m]);
             tma_prefetch_desc(&p.mapB);
             uint32_t git = 0;   // ring position (one per GROUP of G channel blocks), keeps counting across tiles
-            for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x) {
+            int ltp = 0;
+            for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++ltp) {
                 const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
+                KP_TRACE(0, ltp);
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -134,6 +148,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                     }
                     tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it0 * CB, n_off);   // [BN][64] K-major, 128B swizzle
                 }
+                KP_TRACE(1, ltp);
             }
         }
     } else if (warp == 1) {
@@ -141,6 +156,8 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         {
             const uint32_t leader = elect_one() ? 1u : 0u;
             const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+            const uint64_t a_hi = umma_smem_desc(0u, SBO, 16, LAYOUT);
+            const uint64_t b_hi = umma_smem_desc(0u, 1024, 16, 2u);
             uint32_t git = 0;
             int lt = 0;
             for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++lt) {
@@ -150,26 +167,41 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 const int acc = lt & 1;
                 if (lt >= 2) mbar_wait(&tempty[acc], ((lt >> 1) - 1) & 1);   // epilogue drained this buffer
                 tc_fence_after();
+                if (lane == 0) KP_TRACE(2, lt);
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * p.BN);
+                uint32_t accum = 0u;
                 for (int it0 = it_begin; it0 < it_end; it0 += G, ++git) {
                     const int nv = min(G, it_end - it0);
                     const uint32_t st = git % (uint32_t)S;
+                    // A stage always carries 4 MMAs (64 K-elements).  Their descriptors are built BEFORE the wait - the
+                    // single issuing warp runs on the uniform datapath at ~8 cycles per dependent instruction, and a
+                    // dozen instructions between two UTCHMMA cost ~100 cycles per MMA (measured: T_mma ~ 100 + N/2
+                    // cycles for N = 16..256) - so that the MMAs go out back to back once the data has landed.
+                    const uint32_t a16 = (smem_base + st * p.stage_bytes) >> 4;
+                    const uint32_t b16 = a16 + (p.a_bytes >> 4);
+                    uint64_t da[4], db[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        constexpr int KPB = CB / 16;                 // MMAs per channel block
+                        const int g = i / KPB, k = i % KPB;
+                        // A: box g, rows of CB*2 bytes with the matching swizzle; B: 128-byte rows (64 K-elements),
+                        // the 16-element slice of block g / step k sits (g*CB + k*16)*2 bytes into the row
+                        da[i] = a_hi | (uint64_t)(a16 + (uint32_t)((g * (int)A_BOX_BYTES + k * 32) >> 4));
+                        db[i] = b_hi | (uint64_t)(b16 + (uint32_t)(((g * CB + k * 16) * 2) >> 4));
+                    }
+                    const int n_mma = nv * (CB / 16);
                     mbar_wait(&full[st], (git / (uint32_t)S) & 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + st * p.stage_bytes;
-                    const uint32_t b_addr = a_addr + p.a_bytes;
-                    for (int g = 0; g < nv; ++g) {
 #pragma unroll
-                        for (int k = 0; k < CB / 16; ++k) {
-                            // A: box g, rows of CB*2 bytes with the matching swizzle; B: 128-byte rows (64 K-elements),
-                            // the 16-element slice of block g / step k sits (g*CB + k*16)*2 bytes into the row
-                            const uint64_t da = umma_smem_desc(a_addr + g * A_BOX_BYTES + k * 32, SBO, 16, LAYOUT);
-                            const uint64_t db = umma_smem_desc(b_addr + (g * CB + k * 16) * 2, 1024, 16, 2u);
-                            umma_bf16_if(leader, d_tmem, da, db, idesc, ((it0 - it_begin) | g | k) != 0 ? 1u : 0u);
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < n_mma) {
+                            umma_bf16_if(leader, d_tmem, da[i], db[i], idesc, i == 0 ? accum : 1u);
                         }
                     }
+                    accum = 1u;
                     umma_commit_if(leader, &empty[st]);
                 }
+                if (lane == 0) KP_TRACE(3, lt);
                 umma_commit_if(leader, &tfull[acc]);
             }
         }
@@ -198,13 +230,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
             const bool valid = (uw < p.Wo) && (uh < p.Ho) && (n < p.N);
             const long long pix = p.out_off + (long long)n * p.out_sn + (long long)uh * p.out_sh + (long long)uw * p.out_sw;
             const int acc = lt & 1;
+            if (threadIdx.x == 64) KP_TRACE(4, lt);
             mbar_wait(&tfull[acc], (lt >> 1) & 1);
             tc_fence_after();
+            if (threadIdx.x == 64) KP_TRACE(5, lt);
             const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
                 float v[16];
                 __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-pixel predicated stores
                 tmem_ld16(t_row + (uint32_t)c0, v);
+                if (c0 == 0 && threadIdx.x == 64) KP_TRACE(7, lt);
                 if (c0 + 16 >= p.BN) {
                     // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
                     tc_fence_before();
@@ -213,6 +248,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 }
                 epi_chunk(p, v, n_off + c0, valid, pix, lane, ks, s_bias, s_stat);
             }
+            if (threadIdx.x == 64) KP_TRACE(6, lt);
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
@@ -424,7 +460,13 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
         }
         if (p.ksplit == 1) p.groups_per_split = n_groups;
     }
-    p.a_bytes = 128u * 64u * 2u;                       // G = 64/CB activation boxes of 128 x CB
+    {
+        // G = 64/CB activation boxes of 128 x CB per stage - or fewer when the whole K loop is shorter than one stage
+        // (1x1 head: one 4 KB box), which leaves room for more stages / CTAs
+        const int G = 64 / CB;
+        const int boxes = total_iters < G ? total_iters : G;
+        p.a_bytes = ((uint32_t)boxes * 128u * (uint32_t)CB * 2u + 1023u) & ~1023u;
+    }
     p.b_bytes = (uint32_t)BN * 64u * 2u;               // one weight box [BN][64]
     p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
     // CTAs per SM: two independent pipelines per SM hide the barrier round trips of the single-thread TMA / MMA
@@ -434,11 +476,12 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     const uint32_t epi_bytes = 3u * (uint32_t)d->Cout_pad * sizeof(float);
     int ctas_per_sm = p.tmem_cols <= 256 ? 2 : 1;
     if (p.tmem_cols <= 128 && p.groups_per_split <= 8) ctas_per_sm = 3;
+    if (p.tmem_cols <= 128 && p.groups_per_split <= 1) ctas_per_sm = 4;   // one K group per tile: pure epilogue/latency work
     if (const char* e = getenv("KP_TAPCONV_CTAS_PER_SM")) {
         const int want = atoi(e);
-        ctas_per_sm = want >= 3 && p.tmem_cols <= 128 ? 3 : want >= 2 && p.tmem_cols <= 256 ? 2 : 1;
+        ctas_per_sm = want >= 4 && p.tmem_cols <= 128 ? 4 : want >= 3 && p.tmem_cols <= 128 ? 3 : want >= 2 && p.tmem_cols <= 256 ? 2 : 1;
     }
-    uint32_t budget = (ctas_per_sm == 3 ? 70u : ctas_per_sm == 2 ? 108u : 216u) * 1024u - epi_bytes;
+    uint32_t budget = (ctas_per_sm == 4 ? 52u : ctas_per_sm == 3 ? 70u : ctas_per_sm == 2 ? 108u : 216u) * 1024u - epi_bytes;
     if (const char* e = getenv("KP_TAPCONV_SMEM_KB")) budget = (uint32_t)atoi(e) * 1024u;
     int stages = (int)(budget / p.stage_bytes);
     if (stages < 2) stages = 2;
@@ -448,8 +491,15 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
     p.Cout = d->Cout; p.cout_pad = d->Cout_pad; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate;
     p.bias = bias; p.ssum = ssum; p.ssq = ssq;
+    if (getenv("KP_DEBUG_NOSTORE")) p.Cout = 0;   // experiments only: epilogue drains TMEM but stores nothing
 
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024 + epi_bytes;
+    unsigned long long* trace = nullptr;
+    if (getenv("KP_TAPCONV_TRACE")) {
+        cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
+        cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
+    }
+    p.dbg = trace;
     int grid = device_sm_count() * ctas_per_sm;
     if (grid > p.total_tiles * p.ksplit) grid = p.total_tiles * p.ksplit;
 #define KP_LAUNCH_TAPCONV(CBV)                                                                                      \
@@ -467,6 +517,23 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     else KP_LAUNCH_TAPCONV(16);
 #undef KP_LAUNCH_TAPCONV
     KP_LAUNCHED();
+    if (trace != nullptr) {
+        // debug only: synchronise, print the per-tile timeline of CTA 0 (ns relative to the first event)
+        unsigned long long h[24 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 24 * 8; ++i) if (h[i] != 0 && h[i] < t0) t0 = h[i];
+        fprintf(stderr, "tapconv trace grid=%d ctas/sm=%d stages=%d BN=%d tiles=%d iters=%d: tile: prod_start prod_issued mma_start mma_issued epi_wait epi_go epi_done first_ld_done (ns)\n",
+                grid, ctas_per_sm, stages, BN, p.total_tiles, total_iters);
+        for (int t = 0; t < 24; ++t) {
+            if (h[t * 8] == 0) break;
+            fprintf(stderr, "  %2d:", t);
+            for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", h[t * 8 + k] ? (long long)(h[t * 8 + k] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(trace);
+    }
     return KP_OK;
 }
 
