@@ -232,6 +232,10 @@ int kp_bn_stats_apply(const float* stats_sum, const float* stats_sq, const float
 int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
                   const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
                   void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, void* stream);
+/* adjoint of tf.image.resize_images x2 (legacy bilinear, models/networks/__init__.py:63,98) alone:
+ * dout bf16 [N,2H,2W,C] -> dact bf16 [N,H,W,C].  The BN backward of the upsampling layers runs this once and then the
+ * plain (upsample = 0) kp_bn_act_bwd on dact.                                                                 */
+int kp_upsample2x_bwd(const void* dout, int N, int H, int W, int C, void* dact, void* stream);
 /* g = dy * (y > 0 ? 1 : alpha): backward of the fused bias+ReLU / bias+leaky_relu epilogues. */
 int kp_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, void* stream);
 /* tf.nn.max_pool 2x2 s2 (models/networks/vgg.py:45-46) and its backward (gradient to the first maximum; with

@@ -328,6 +328,35 @@ def test_pack_weights_kernel_matches_recipe(cuda_dev):
             c0 += sh[3]
 
 
+def test_batched_pack_matches_single_launch_pack(cuda_dev):
+    """kp_pack_weights_batch (one launch for a whole job table, in place) == kp_pack_weights per job, bit-exact: forward
+    (concat segments, tails, unpadded cin/cout) and data-gradient layouts (vector path cout % 8 == 0 and scalar path)."""
+    from kp_b200 import conv, tapconv as tc
+    rng = np.random.default_rng(33)
+    jobs, refs = [], []
+    cases = [([(2, 8, 8, 16), (2, 8, 8, 32)], 3, 1, 0, 24), ([(1, 8, 8, 40)], 3, 1, 0, 16), ([(1, 16, 16, 64)], 4, 2, 1, 128),
+             ([(1, 8, 8, 16)], 7, 1, 0, 32), ([(1, 8, 8, 128), (1, 8, 8, 40), (1, 8, 8, 40)], 3, 1, 0, 256),
+             ([(1, 8, 8, 64)], 3, 1, 0, 4), ([(1, 8, 8, 2048)], 3, 1, 1, 1), ([(1, 8, 8, 256)], 3, 1, 0, 512)]
+    for shapes, k, s, pad, cout in cases:
+        cin = sum(sh[3] for sh in shapes)
+        wd = torch.from_numpy(rng.normal(size=(k, k, cin, cout)).astype(np.float32)).to(cuda_dev)
+        plan, _ = tc.plan_conv_fwd(shapes, k, s, pad, cout)
+        plans = [plan]
+        c0 = 0
+        cpad = (cout + 7) // 8 * 8
+        for sh in shapes:
+            plans += list(tc.plan_conv_dgrad(sh, k, s, pad, cpad, cin_slice=(c0, c0 + sh[3], cin)))
+            c0 += sh[3]
+        for pl in plans:
+            refs.append(conv.pack_weights(pl, wd))
+            jobs.append((pl, wd, torch.full_like(refs[-1], float("nan"))))
+    table = conv.PackTable(jobs, cuda_dev)
+    table.run()
+    torch.cuda.synchronize()
+    for (pl, _, out), ref in zip(jobs, refs):
+        assert torch.equal(out.view(torch.int16), ref.view(torch.int16)), (pl.pack["mode"], pl.rows_pad, pl.Ktot)
+
+
 @pytest.mark.parametrize("k,cpad,cout,with_bn", [(7, 32, 32, True), (3, 16, 64, False)])
 def test_w_unrolled_first_layer_matches_square_conv(cuda_dev, k, cpad, cout, with_bn):
     """The 3-channel first layers run as k x 1 convolutions over a W-unrolled image (kp_image_prep_unrolled): forward,

@@ -39,6 +39,7 @@ SIGNATURES = {
                        c_vp, c_vp, c_vp],
     "kp_bn_stats_apply": [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_float, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                           c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "kp_upsample2x_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_apply": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                       c_vp, c_vp, c_int, c_vp],

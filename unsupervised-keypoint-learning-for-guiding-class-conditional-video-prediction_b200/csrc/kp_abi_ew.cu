@@ -62,6 +62,11 @@ int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const flo
     return ew_bn_act_bwd(dout, x, scale, shift, save_mean, save_rstd, relu, upsample, N, H, W, C, dbeta, dgamma, dx, gbeta_acc,
                          ggamma_acc, prezeroed, ST);
 }
+int kp_upsample2x_bwd(const void* dout, int N, int H, int W, int C, void* dact, void* stream) {
+    KP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", __func__);
+    KP_NONNULL(dout); KP_NONNULL(dact);
+    return ew_upsample2x_bwd(dout, N, H, W, C, dact, ST);
+}
 int kp_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, void* stream) {
     KP_NONNEG(n_elems);
     if (n_elems == 0) return KP_OK;

@@ -61,6 +61,7 @@ int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int r
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
                   const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
                   void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, cudaStream_t st);
+int ew_upsample2x_bwd(const void* dout, int N, int H, int W, int C, void* dact, cudaStream_t st);
 int ew_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, cudaStream_t st);
 int ew_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, cudaStream_t st);
 int ew_maxpool_bwd(const void* dy, const void* x, int relu_mask, int N, int H, int W, int C, void* dx, cudaStream_t st);

@@ -113,8 +113,14 @@ def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False, gbe
         dgamma = torch.empty(C, device=x.device, dtype=F32)
         pre = 0
     dx = torch.empty_like(x)
+    if upsample:
+        # adjoint of the x2 resize once (kp_upsample2x_bwd), then the plain backward: the fused variant gathered the 3x3
+        # neighbourhood of dout in BOTH of its passes
+        dact = torch.empty_like(x)
+        _lib.call("kp_upsample2x_bwd", _p(dout), N, H, W, C, _p(dact), _st())
+        dout = dact
     _lib.call("kp_bn_act_bwd", _p(dout), _p(x), _p(scale), _p(shift), _p(mean), _p(rstd), 1 if relu else 0,
-              1 if upsample else 0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _p(gbeta_acc), _p(ggamma_acc), pre, _st())
+              0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _p(gbeta_acc), _p(ggamma_acc), pre, _st())
     return dx, dgamma, dbeta
 
 
