@@ -11,6 +11,7 @@ names) and its step semantics:
 Data parallelism: one process per GPU; gradients of the flat G / D buffers are summed with one NCCL all-reduce
 each per step and scaled by 1/world_size inside the Adam kernel; BN statistics stay per replica.
 """
+import os
 import time
 from datetime import datetime
 
@@ -50,6 +51,9 @@ class DetectorTranslatorModel(BaseModel):
         self._graph = None
         self._lr_dev = None
         self._static = None
+        self._side = None                  # side stream for the overlapped discriminator update (data parallel only)
+        self._d_pending = False
+        self.overlap_d_update = os.environ.get("KP_OVERLAP_D_UPDATE", "1") != "0"
         # outputs of the last forward pass (names follow the reference's attributes)
         self.final_output = self.crude_output = self.mask = None
         self.current_keypoints = self.future_keypoints = None
@@ -168,6 +172,7 @@ class DetectorTranslatorModel(BaseModel):
             ops.l1_pair(fg, fp, 1.0 / len(feat_pred), loss[0:1], d)
             if backward:
                 tape.set_grad(fp, d)
+        self._join_D()                      # the discriminator update of the D run must have landed
         fake_ = networks.img_discr(future_im_pred, need_input_grad=backward)
         d_adv = ops.bce_logits(fake_, 1.0, 1.0, loss[1:2], backward)
         if backward:
@@ -189,12 +194,33 @@ class DetectorTranslatorModel(BaseModel):
         loss = self._compute_loss_D(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.train_D = None, False
+        if self.world > 1 and self.overlap_d_update:
+            # Data parallel: the 179 MB all-reduce of the discriminator gradients, Adam(D) and the D weight re-pack run on
+            # a side stream while the G run's generator forward (which does not touch img_discr) proceeds; the streams
+            # join right before the G run's D(fake) (_join_D).  Inside the captured graph this is a fork/join of nodes.
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._finish_D()
+            self._d_pending = True
+        else:
+            self._finish_D()
+        return loss
+
+    def _finish_D(self):
+        ctx = self.ctx
         self._allreduce(ctx.D.grad)
         self.t_D += 1
         ops.adam_tf(ctx.D.data, ctx.D.grad, ctx.D.m, ctx.D.v, self._current_lr(), self.t_D, grad_scale=1.0 / self.world,
                     lr_t_dev=self._lr_dev[0:1] if self._lr_dev is not None else None)
         ctx.params_changed(ctx.D)
-        return loss
+
+    def _join_D(self):
+        if self._d_pending:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._d_pending = False
 
     def _run_G(self, im, future_im):
         ctx = self.ctx
@@ -205,6 +231,7 @@ class DetectorTranslatorModel(BaseModel):
         loss = self._compute_loss_G(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.update_moving, ctx.train_G = None, False, False
+        self._join_D()
         self._allreduce(ctx.G.grad)
         self.t_G += 1
         ops.adam_tf(ctx.G.data, ctx.G.grad, ctx.G.m, ctx.G.v, self._current_lr(), self.t_G, grad_scale=1.0 / self.world,
