@@ -151,3 +151,19 @@ def test_final_model_outputs(cuda_dev):
     with pytest.raises(NotImplementedError):
         fm.build({"image": im.to(cuda_dev)})
         fm.run()
+
+
+def test_device_prefetcher_preserves_order_and_values(cuda_dev):
+    from kp_b200.utils import DevicePrefetcher
+    host = [{"image": torch.full((2, 4, 4, 3), float(i)).pin_memory(), "future_image": torch.full((2, 4, 4, 3), -float(i)).pin_memory()}
+            for i in range(5)]
+    cur = {"i": -1}
+
+    def feed():
+        cur["i"] += 1
+        return host[cur["i"] % 5]
+    pf = DevicePrefetcher(feed, cuda_dev, depth=2)
+    for i in range(12):
+        b = pf()
+        assert b["image"].is_cuda and float(b["image"][0, 0, 0, 0]) == float(i % 5)
+        assert float(b["future_image"][1, 3, 3, 2]) == -float(i % 5)
