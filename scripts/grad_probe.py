@@ -102,6 +102,7 @@ PERF = {
     "packed4_head": (32, 128, 32, [64], 1, 1, 160),
     "packed2_32_32_64sq": (32, 64, 32, [64], 3, 1, 64),
     "det_64_32": (32, 64, 64, [32], 3, 1, 32),
+    "trans5_128_128_64": (32, 128, 128, [128], 3, 1, 64),
     "heads_128_64_8": (32, 128, 128, [64], 3, 1, 8),
     "enc1_128_32_32_7x1": (32, 128, 128, [32], (7, 1), 1, 32),
     "dec_64_96_32": (32, 64, 64, [32, 64], 3, 1, 32),

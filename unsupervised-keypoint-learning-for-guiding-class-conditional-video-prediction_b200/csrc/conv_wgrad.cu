@@ -15,6 +15,7 @@
 #include "kp_tc.cuh"
 #include "kp_internal.h"
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace kp {
@@ -34,7 +35,19 @@ struct alignas(64) WgradKParams {
     uint32_t box_bytes, ybox_bytes, stage_bytes;
     float* dw_out;
     long long dw_off, dw_stap, dw_sci;
+    unsigned long long* dbg;   // KP_TAPCONV_TRACE: per-stage timestamps of CTA (0,0,0) (debug only)
 };
+
+__device__ __forceinline__ unsigned long long wg_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KP_WTRACE(slot, idx)                                                                                              \
+    do {                                                                                                                  \
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 24) p.dbg[(idx) * 8 + (slot)] = wg_gtime(); \
+    } while (0)
+
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -96,30 +109,39 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     pdl_wait();
 
     if (warp == 0) {
+        // TMA producer, the WHOLE warp: each lane issues the boxes b = lane, lane+32, ... of a stage.  One thread issuing
+        // the 7-19 loads of a stage one after the other was the bottleneck of the weight gradient (timeline trace:
+        // ~600 ns of issue per 56 KB stage = 30 B/clk/SM, well under the 50 B/clk/SM fill rate).
         if (lane == 0) {
             tma_prefetch_desc(&p.mapDY);
             for (int m = 0; m < KP_MAX_MAPS; ++m)
                 if (m == 0 || p.mf[tap0] == m) tma_prefetch_desc(&p.mapX[m]);
-            const uint32_t tx = (uint32_t)(nt * n_a) * p.box_bytes + (uint32_t)n_b * p.ybox_bytes;
-            for (int it = 0; it < n_iters; ++it) {
-                const int tile = t_begin + it;
-                const int w0 = (tile % p.tiles_w) * p.TW;
-                const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
-                const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
-                const int st = it % S;
-                if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
-                uint8_t* dy_dst = base + (size_t)st * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[st], tx);
-                for (int c = 0; c < n_b; ++c)
-                    tma_load_4d(dy_dst + (size_t)c * p.ybox_bytes, &p.mapDY, &full[st], co0 + c * CBY, w0, h0, n0);
-                for (int ti = 0; ti < nt; ++ti) {
+        }
+        const uint32_t tx = (uint32_t)(nt * n_a) * p.box_bytes + (uint32_t)n_b * p.ybox_bytes;
+        const int n_boxes = n_b + nt * n_a;
+        for (int it = 0; it < n_iters; ++it) {
+            const int tile = t_begin + it;
+            const int w0 = (tile % p.tiles_w) * p.TW;
+            const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+            const int n0 = (tile / (p.tiles_w * p.tiles_h)) * p.TN;
+            const int st = it % S;
+            if (it >= S) mbar_wait(&empty[st], ((it / S) - 1) & 1);
+            if (lane == 0) KP_WTRACE(0, it);
+            uint8_t* dy_dst = base + (size_t)st * p.stage_bytes;
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], tx);
+            __syncwarp();                                  // the expected byte count is registered before any copy can land
+            for (int bx = lane; bx < n_boxes; bx += 32) {
+                if (bx < n_b) {
+                    tma_load_4d(dy_dst + (size_t)bx * p.ybox_bytes, &p.mapDY, &full[st], co0 + bx * CBY, w0, h0, n0);
+                } else {
+                    const int j = bx - n_b;
+                    const int ti = j / n_a, c = j - ti * n_a;
                     const int t = tap0 + ti;
-                    uint8_t* x_dst = dy_dst + dy_region + (size_t)ti * x_region;
-                    for (int c = 0; c < n_a; ++c)
-                        tma_load_4d(x_dst + (size_t)c * p.box_bytes, &p.mapX[p.mf[t]], &full[st], ci0 + c * CB, w0 + p.dw[t],
-                                    h0 + p.dh[t], n0);
+                    tma_load_4d(dy_dst + dy_region + (size_t)ti * x_region + (size_t)c * p.box_bytes, &p.mapX[p.mf[t]], &full[st],
+                                ci0 + c * CB, w0 + p.dw[t], h0 + p.dh[t], n0);
                 }
             }
+            if (lane == 0) KP_WTRACE(1, it);
         }
     } else if (warp == 1) {
         {
@@ -129,6 +151,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                 const int st = it % S;
                 mbar_wait(&full[st], (it / S) & 1);
                 tc_fence_after();
+                if (lane == 0) KP_WTRACE(2, it);
                 const uint32_t dy_addr = smem_base + (uint32_t)st * p.stage_bytes;
                 // One M=128 MMA reads 128/CB consecutive X boxes: with Cin <= 64 these are the boxes of R consecutive
                 // taps (rows = (tap, channel)), so ONE accumulator serves R taps and the MMA count drops R-fold.
@@ -142,6 +165,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
                         umma_bf16_if(leader, d_tmem, da, db, idesc, (it | kk) != 0 ? 1u : 0u);
                     }
                 }
+                if (lane == 0) KP_WTRACE(3, it);
                 umma_commit_if(leader, &empty[st]);
             }
             umma_commit_if(leader, tfull);
@@ -268,6 +292,12 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 1) * 8 + 16 + 1024 + slack;
     KP_REQUIRE(smem <= 227u * 1024u, "kp_wgrad: shared memory %zu exceeds the SM (internal tiling error)", smem);
     dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)groups, (unsigned)splits);
+    unsigned long long* trace = nullptr;
+    if (getenv("KP_TAPCONV_TRACE")) {
+        cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
+        cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
+    }
+    p.dbg = trace;
 #define KP_LAUNCH_WGRAD(CBX, CBYV)                                                                                  \
     do {                                                                                                            \
         static bool attr_done = false;                                                                              \
@@ -290,6 +320,22 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
 #undef KP_LAUNCH_WGRAD_Y
 #undef KP_LAUNCH_WGRAD
     KP_LAUNCHED();
+    if (trace != nullptr) {
+        unsigned long long h[24 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 24 * 8; ++i) if (h[i] != 0 && h[i] < t0) t0 = h[i];
+        fprintf(stderr, "wgrad trace grid=(%u,%u,%u) CB=%d CBY=%d T=%d R=%d BN=%d stages=%d stage_bytes=%u tiles/split=%d: stage: prod_go prod_issued "
+                "mma_data mma_issued (ns)\n", grid.x, grid.y, grid.z, CB, CBY, p.T, p.R, p.BN, stages, p.stage_bytes, p.tiles_per_split);
+        for (int t = 0; t < 24; ++t) {
+            if (h[t * 8] == 0) break;
+            fprintf(stderr, "  %2d:", t);
+            for (int k = 0; k < 4; ++k) fprintf(stderr, " %7lld", h[t * 8 + k] ? (long long)(h[t * 8 + k] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(trace);
+    }
     return KP_OK;
 }
 
