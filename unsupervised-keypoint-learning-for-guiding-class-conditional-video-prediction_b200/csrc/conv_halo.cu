@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) haloconv_kernel(const __grid_
     uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_bias = reinterpret_cast<float*>(tslot + 4);
     float* s_stat = s_bias + p.cout_pad;
-    uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_stat + 2 * p.cout_pad);   // [n_taps] halo offsets in 16-byte units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_rows = 16 * HALVES;

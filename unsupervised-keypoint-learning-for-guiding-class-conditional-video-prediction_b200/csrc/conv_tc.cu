@@ -369,6 +369,8 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     if (encode == nullptr) return KP_ERR_DRIVER;
     // stride-1 multi-tap layers: halo-tile kernel (each input element is fetched once per tile instead of once per tap)
     if (haloconv_eligible(d, ssum)) return haloconv_launch(d, src, wpacked, bias, out, ssum, ssq, st);
+    // wide layers, experimental: CTA pairs (cta_group::2) halve the weight fill per SM
+    if (tapconv2_eligible(d)) return tapconv2_launch(d, src, wpacked, bias, out, ssum, ssq, st);
 
     TapConvKParams p;
     memset(&p, 0, sizeof(p));
