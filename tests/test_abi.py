@@ -47,3 +47,33 @@ def test_python_mirror_rejects_cpu_tensors(lib_built):
         model_utils.get_gaussian_maps(torch.zeros(1, 40, 2), [32, 32])
     with pytest.raises(ValueError):
         model_utils.get_coord(torch.zeros(1, 8, 8, 4), 2, 8)
+
+
+def test_argument_validation_of_conv_and_bn_entry_points(lib_built):
+    """NULL pointers / bad shapes of the convolution-side entry points are rejected with rc -1 and a message naming the
+    argument, before any CUDA call (so this runs without a GPU)."""
+    import ctypes as C
+    L = lib_built._lib
+    h = L.load()
+    from kp_b200 import tapconv as tc
+    # kp_bn_stats_apply: NULL statistics
+    rc = h.kp_bn_stats_apply(None, None, None, None, None, 16.0, 1e-5, 0.999, None, None, None, None, None, None, None, 1, 0,
+                             1, 4, 4, 16, None, None)
+    assert rc == -1 and b"kp_bn_stats_apply" in h.kp_last_error()
+    # kp_upsample2x_bwd: bad shape, then NULL tensors
+    assert h.kp_upsample2x_bwd(None, 0, 4, 4, 16, None, None) == -1
+    assert h.kp_upsample2x_bwd(None, 1, 4, 4, 16, None, None) == -1
+    # kp_pack_weights_batch: NULL job table
+    assert h.kp_pack_weights_batch(None, 1, 1, None) == -1
+    # kp_pack_job_blocks: malformed descriptor -> 0 blocks, well-formed forward descriptor -> tiles of 64 x 32
+    d = tc.PackDesc()
+    assert h.kp_pack_job_blocks(C.byref(d)) == 0
+    plan, _ = tc.plan_conv_fwd([(1, 8, 8, 64)], 3, 1, 0, 128)
+    d = tc.pack_desc(plan, (3, 3, 64, 128))
+    assert h.kp_pack_job_blocks(C.byref(d)) == 9 * ((64 + 63) // 64) * ((128 + 31) // 32)
+    # kp_tapconv_bf16: a descriptor with an unsupported channel block
+    td = plan.desc()
+    td.CB = 24
+    ptrs = (C.c_void_p * tc.KP_MAX_MAPS)()
+    rc = h.kp_tapconv_bf16(C.byref(td), ptrs, None, None, None, None, None, None)
+    assert rc == -1
