@@ -31,6 +31,9 @@ if ROOT not in sys.path:
 
 K1_BYTES_PER_FRAME = 128 * 128 * 40 * 4 + 32 * 32 * 40 * 4 + 40 * 2 * 4   # 2 785 600
 TRAIN_GFLOP_PER_EXAMPLE = 152.369                                          # SURVEY.md §8d config 3 (useful conv work)
+TRAIN_WORKLOAD = ("BASELINE configs[2]: stage-1 detector_translator train_step (D run + G run on different batches, fwd+bwd incl. "
+                  "VGG19 perceptual loss + img_discr, 2x Adam), random-init incl. VGG19")
+K1_WORKLOAD = "BASELINE configs[1]: fused soft-argmax + Gaussian render, [128,128,40] fp32 logits -> mu [40,2] + maps [32,32,40]"
 CONFIG = {"paths": {"data_dir": "", "vggnet": None, "log_dir": "/tmp/kp_b200_logs"},
           "training": {"batch_size": 32, "lr": {"start_val": 1e-4, "step": 20000, "decay": 0.95}},
           "model": {"n_pts": 40, "n_action": 9, "cell_info": [1024, 1024], "vae_dim": 64}}
@@ -203,14 +206,14 @@ def run_reference(args):
         vals = [cpu_k1(8, workers, 1) for _ in range(max(args.warmup, 1) + min(args.steps, 10))][max(args.warmup, 1):]
         v, cores = statistics.median(vals), workers
         sample = "%d steps x %d frames (%d procs), numpy fp32 oracle of utils/model.py" % (len(vals), 8 * workers, workers)
-        metric, wl, steps, ms = "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "k1", len(vals), 1e3 * 8 * workers / v
+        metric, wl, steps, ms = "stage-1 frames/sec (fused soft-argmax + Gaussian render)", K1_WORKLOAD, len(vals), 1e3 * 8 * workers / v
     else:
         b = args.cpu_batch
         steps = max(1, min(args.steps, args.cpu_steps))
         v, cores, sec = cpu_train(b, steps, warmup=1)
         sample = ("%d train_steps (D run + G run, fwd+bwd incl. VGG19, TF Adam) at batch %d instead of 32: torch-CPU fp32 "
                   "oracle of the reference graph, %d threads" % (steps, b, cores))
-        metric, wl, ms = "stage-1 frames/sec (train_step: D run + G run)", "train", sec * 1e3
+        metric, wl, ms = "stage-1 frames/sec (train_step: D run + G run)", TRAIN_WORKLOAD, sec * 1e3
     emit({
         "impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,8 +394,7 @@ def bench_k1(args, world, rank, dev, lib):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
-    return {"workload": "BASELINE configs[1]: fused soft-argmax + Gaussian render, %d frames/GPU [128,128,40] fp32 -> "
-                        "mu [40,2] + maps [32,32,40]; input 2.68 GB per launch >> 126 MB L2" % B,
+    return {"workload": K1_WORKLOAD, "frames_per_gpu": B, "l2": "input 2.68 GB per launch >> 126 MB L2",
             "frames_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
             "gpu_launches": int(lib.kp_launch_count() - n0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -419,7 +421,7 @@ def run_ours(args):
             emit({"metric": "stage-1 frames/sec (fused soft-argmax + Gaussian render)", "value": r["frames_per_s"],
                               "unit": "frames/s", "n_gpus": world, "steps": r["steps"], "warmup": args.warmup,
                               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                              "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"]},
+                              "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"], "frames_per_gpu": r["frames_per_gpu"], "l2": r["l2"]},
                               "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]})
         if world > 1:
             torch.distributed.barrier()
@@ -573,8 +575,7 @@ def run_ours(args):
             "metric": "stage-1 frames/sec (train_step: D run + G run)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: stage-1 detector_translator train_step (D run + G run on different "
-                                   "batches, fwd+bwd incl. VGG19 perceptual loss + img_discr, 2x Adam), random-init incl. VGG19",
+            "config": {"workload": TRAIN_WORKLOAD,
                        "batch_per_gpu": B, "frames_per_step_per_gpu": frames_per_step, "image_hw": [128, 128], "n_pts": 40,
                        "examples_per_s": world * B / (ms_per_step * 1e-3), "parallelism": "dp%d" % world,
                        "cuda_graph": not args.no_graph,
