@@ -458,3 +458,55 @@ def test_halo_tile_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypa
         for got in (st_halo, st_tap):
             assert (got[0][:cout].double() - s_ref).abs().max().item() <= 2e-3 * (s_ref.abs().max().item() + ref.abs().sum(dim=(0, 1, 2)).max().item() * 1e-2)
             assert (got[1][:cout].double() - q_ref).abs().max().item() <= 2e-3 * q_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("geom", [(2, 32, 32, 16, 32, 16, 3), (2, 16, 16, 64, 128, 64, 3), (3, 24, 20, 32, 64, 8, 1)])
+def test_two_layer_chain_forward_backward(cuda_dev, geom):
+    """conv1 + BN + ReLU -> conv2 + BN + ReLU through the tape: every gradient against the fp64 autograd oracle on the same
+    bf16-rounded operands (the data gradient of layer 2 feeds the batch-norm backward of layer 1)."""
+    from kp_b200 import engine as E
+    N, H, W, C0, C1, C2, k2 = geom
+    rng = np.random.default_rng(C0 + C1 + C2)
+    x = torch.from_numpy(rng.normal(size=(N, H, W, C0)).astype(np.float32)).to(BF)
+    w1 = torch.from_numpy((rng.normal(size=(3, 3, C0, C1)) / np.sqrt(9 * C0)).astype(np.float32)).to(BF).float()
+    w2 = torch.from_numpy((rng.normal(size=(k2, k2, C1, C2)) / np.sqrt(k2 * k2 * C1)).astype(np.float32)).to(BF).float()
+    b1 = torch.from_numpy(rng.normal(0, 0.1, C1).astype(np.float32))
+    b2 = torch.from_numpy(rng.normal(0, 0.1, C2).astype(np.float32))
+    g1 = torch.from_numpy(rng.uniform(0.5, 1.5, C1).astype(np.float32)); be1 = torch.from_numpy(rng.normal(0, 0.3, C1).astype(np.float32))
+    g2 = torch.from_numpy(rng.uniform(0.5, 1.5, C2).astype(np.float32)); be2 = torch.from_numpy(rng.normal(0, 0.3, C2).astype(np.float32))
+    ctx = _mk_ctx(cuda_dev, {"a/conv2d/kernel": w1, "a/conv2d/bias": b1, "b/conv2d/kernel": w2, "b/conv2d/bias": b2},
+                  {"bna": C1, "bnb": C2})
+    for n_, v in (("bna/gamma", g1), ("bna/beta", be1), ("bnb/gamma", g2), ("bnb/beta", be2)):
+        ctx.G.p(n_).copy_(v.to(cuda_dev))
+    ctx.S.p("bna/moving_variance").fill_(1.0); ctx.S.p("bnb/moving_variance").fill_(1.0)
+    ctx.params_changed()
+    ctx.begin_run()
+    ctx.tape, ctx.train_G = E.Tape(), True
+    xd = x.to(cuda_dev)
+    h1 = E.conv_layer(ctx, [xd], "a/conv2d/kernel", "a/conv2d/bias", 3, 1, 0, bn="bna", train_mode=True)
+    h2 = E.conv_layer(ctx, [h1], "b/conv2d/kernel", "b/conv2d/bias", k2, 1, 0, bn="bnb", train_mode=True)
+    dout = torch.from_numpy(rng.normal(size=tuple(h2.shape)).astype(np.float32)).to(BF)
+    ctx.tape.set_grad(h2, dout.to(cuda_dev))
+    tape = ctx.tape
+    for fn in reversed(tape.ops):
+        fn()
+    dx = tape.grad(xd)
+    # oracle
+    x64 = x.double().requires_grad_(True)
+    P = {n_: v.double().requires_grad_(True) for n_, v in (("w1", w1), ("w2", w2), ("b1", b1), ("b2", b2), ("g1", g1), ("be1", be1),
+                                                           ("g2", g2), ("be2", be2))}
+    y1 = T.conv2d(x64, P["w1"], P["b1"], 1, 0)
+    z1, _, _ = T.batch_norm(y1, P["g1"], P["be1"], torch.zeros(C1, dtype=torch.float64), torch.ones(C1, dtype=torch.float64), True)
+    a1 = torch.relu(z1)
+    y2 = T.conv2d(a1, P["w2"], P["b2"], 1, 0)
+    z2, _, _ = T.batch_norm(y2, P["g2"], P["be2"], torch.zeros(C2, dtype=torch.float64), torch.ones(C2, dtype=torch.float64), True)
+    a2 = torch.relu(z2)
+    a2.backward(dout.double())
+    _close(h2, a2.detach(), 2e-2, "forward")
+    # layer-1 quantities sit behind two ReLU masks and two batch-statistics renormalisations: 1.5x the single-layer budget
+    _close(ctx.G.g("bna/gamma"), P["g1"].grad, 1.5e-2, "dgamma layer 1")
+    _close(ctx.G.g("bna/beta"), P["be1"].grad, 1.5e-2, "dbeta layer 1")
+    _close(ctx.G.g("bnb/gamma"), P["g2"].grad, 1e-2, "dgamma layer 2")
+    _close(ctx.G.g("a/conv2d/kernel"), P["w1"].grad, 1.5e-2, "dW layer 1")
+    _close(ctx.G.g("b/conv2d/kernel"), P["w2"].grad, 1e-2, "dW layer 2")
+    _close(dx, x64.grad, 1.5e-2, "dX")
