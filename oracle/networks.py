@@ -14,6 +14,7 @@ import torch
 
 from . import tf_ops as T
 from . import k1_torch
+from . import precision
 
 VGG_LAYERS = [("conv1_1", 3, 64), ("conv1_2", 64, 64), ("conv2_1", 64, 128), ("conv2_2", 128, 128),
               ("conv3_1", 128, 256), ("conv3_2", 256, 256), ("conv3_3", 256, 256), ("conv3_4", 256, 256),
@@ -147,36 +148,94 @@ def randomize_bn(P, seed=1):
 # networks
 # ------------------------------------------------------------------------------------------------
 class Ctx:
-    """Carries the parameter dict and collects BN moving-average updates (TF's UPDATE_OPS)."""
+    """Carries the parameter dict and collects BN moving-average updates (TF's UPDATE_OPS).
 
-    def __init__(self, params):
+    `q` is the precision model (oracle/precision.py): `Exact` (default) is the reference's float arithmetic;
+    `Bf16Faithful` additionally rounds to bf16 at the points where the B200 path stores bf16 (weights as the tensor
+    cores read them, stored activations, stored activation gradients), which turns a whole-step comparison into a test
+    of the wiring instead of a measurement of bf16 drift."""
+
+    def __init__(self, params, q=None, sub=None):
         self.P = params
+        self.q = q if q is not None else precision.Exact()
         self.updates = []   # [(name, new_value)] in graph order; two entries per BN for the shared pose_encoder
         self.taps = {}      # optional: named intermediate activations
+        # Forward substitution ("teacher forcing", tests only): name -> list of tensors recorded from the implementation
+        # under test, consumed in call order.  s(name, x) returns a tensor with the recorded VALUE and x's gradient
+        # path, and logs how far x (computed here from the substituted inputs) was from it.  With every stored tensor
+        # substituted, ReLU / max-pool / L1-sign decisions and BN statistics are those of the implementation under
+        # test, so the backward passes can be compared without the chaotic divergence of two bf16 forward passes.
+        self.sub = sub
+        self.sub_err = {}
+
+    def s(self, name, x):
+        if self.sub is None or name not in self.sub:
+            return x
+        if not self.sub[name]:
+            raise KeyError("substitution list for %r is exhausted" % name)
+        v = self.sub[name].pop(0).to(x.dtype)
+        if tuple(v.shape) != tuple(x.shape):
+            raise ValueError("substitution %r: shape %r vs %r" % (name, tuple(v.shape), tuple(x.shape)))
+        xd = x.detach()
+        self.sub_err.setdefault(name, []).append(
+            (float((xd - v).norm() / (v.norm() + 1e-300)), float((xd - v).abs().max()), float(v.abs().max())))
+        return x + (v - xd)
 
     def conv(self, x, scope, stride=1, pad=0, use_bias=True):
         b = self.P[scope + "/conv2d/bias"] if use_bias else None
-        return T.conv2d(x, self.P[scope + "/conv2d/kernel"], b, stride, pad)
+        return T.conv2d(x, self.q.w(self.P[scope + "/conv2d/kernel"]), b, stride, pad)
 
     def bn(self, x, scope, train_mode):
         P = self.P
-        y, mm, mv = T.batch_norm(x, P[scope + "/gamma"], P[scope + "/beta"], P[scope + "/moving_mean"],
-                                 P[scope + "/moving_variance"], train_mode)
+        if train_mode and not isinstance(self.q, precision.Exact):
+            # B200 path: statistics from the fp32 accumulators, applied to the bf16-stored convolution output; the
+            # gradient leaving the BN backward is stored as bf16 (one rounding of the complete dy)
+            x = self.q.g(x)
+            n = x.shape[0] * x.shape[1] * x.shape[2]
+            mean = x.mean(dim=(0, 1, 2))
+            var = ((x - mean) ** 2).mean(dim=(0, 1, 2))
+            cs = getattr(self, "_conv_scope", scope)
+            mean_s, rstd_s = self.s(cs + ":mean", mean), self.s(cs + ":rstd", torch.rsqrt(var + 1e-5))
+            y = (self.s(cs + ":pre", self.q.w(x)) - mean_s) * rstd_s * P[scope + "/gamma"] + P[scope + "/beta"]
+            mm = P[scope + "/moving_mean"] * 0.999 + mean.detach() * (1 - 0.999)
+            mv = P[scope + "/moving_variance"] * 0.999 + (var * (n / max(n - 1, 1))).detach() * (1 - 0.999)
+        else:
+            y, mm, mv = T.batch_norm(x, P[scope + "/gamma"], P[scope + "/beta"], P[scope + "/moving_mean"],
+                                     P[scope + "/moving_variance"], train_mode)
         if train_mode:
             self.updates.append((scope + "/moving_mean", mm))
             self.updates.append((scope + "/moving_variance", mv))
         return y
 
-    def cbr(self, x, conv_scope, bn_scope, train_mode, stride=1):
-        y = torch.relu(self.bn(self.conv(x, conv_scope, stride), bn_scope, train_mode))
+    def cbr(self, x, conv_scope, bn_scope, train_mode, stride=1, store=True):
+        """conv + BN + ReLU.  store=False: the caller applies an x2 resize before the result is stored."""
+        c = self.conv(x, conv_scope, stride)
+        self.taps[conv_scope + ":pre"] = c
+        self._conv_scope = conv_scope
+        y = torch.relu(self.bn(c, bn_scope, train_mode))
+        if store:
+            y = self.s(conv_scope, self.q.a(y))
         self.taps[conv_scope] = y
         return y
+
+    def upsample2x(self, x, conv_scope):
+        """tf.image.resize_images x2 of a cbr(..., store=False) result; rounding points of the fused B200 kernel: the
+        gradient arriving at the un-resized activation and the stored resized activation."""
+        size = x.shape[1]
+        y = self.s(conv_scope, self.q.a(T.resize_bilinear_legacy(self.q.g(x), 2 * size, 2 * size)))
+        self.taps[conv_scope + ":up"] = y
+        return y
+
+    def conv_act(self, x, scope, act, stride=1, pad=0, use_bias=True):
+        """conv + bias + pointwise activation stored as bf16 (VGG, img_discr): the masked gradient is stored too."""
+        return self.s(scope, self.q.a(act(self.q.g(self.conv(x, scope, stride, pad, use_bias)))))
 
 
 def encoder(ctx, x, train_mode, prefix):
     """networks/__init__.py:7-26."""
     feats = []
     p = prefix + "encoder/"
+    x = ctx.q.a(x)
     x = ctx.cbr(x, p + "conv_1", p + "b_norm_1", train_mode)
     x = ctx.cbr(x, p + "conv_2", p + "b_norm_2", train_mode)
     feats.append(x)
@@ -205,11 +264,11 @@ def pose_encoder_logits(ctx, x, n_pts, train_mode, final_res=128, filters=128):
         x = ctx.cbr(x, s + "conv_%d_0" % conv_id, s + "b_norm_%d_0" % conv_id, train_mode)
         x = ctx.cbr(x, s + "conv_%d_1" % conv_id, s + "b_norm_%d_1" % conv_id, train_mode)
         if size == final_res:
-            x = ctx.conv(x, s + "conv_0")
+            x = ctx.s(s + "conv_0", ctx.q.g(ctx.conv(x, s + "conv_0")))
             break
         x = ctx.cbr(x, s + "conv_%d_0" % (conv_id + 1), s + "b_norm_%d_0" % (conv_id + 1), train_mode)
-        x = ctx.cbr(x, s + "conv_%d_1" % (conv_id + 1), s + "b_norm_%d_1" % (conv_id + 1), train_mode)
-        x = T.resize_bilinear_legacy(x, 2 * size, 2 * size)
+        x = ctx.cbr(x, s + "conv_%d_1" % (conv_id + 1), s + "b_norm_%d_1" % (conv_id + 1), train_mode, store=False)
+        x = ctx.upsample2x(x, s + "conv_%d_1" % (conv_id + 1))
         size = x.shape[1]
         conv_id += 2
         if filters >= 8:
@@ -220,7 +279,7 @@ def pose_encoder_logits(ctx, x, n_pts, train_mode, final_res=128, filters=128):
 def pose_encoder(ctx, x, n_pts, train_mode, final_res=128, filters=128):
     """networks/__init__.py:36-72 -> mu [B,n_pts,2]."""
     logits = pose_encoder_logits(ctx, x, n_pts, train_mode, final_res, filters)
-    return k1_torch.soft_argmax(logits)
+    return ctx.s("mu", k1_torch.soft_argmax(logits))
 
 
 def translator(ctx, x, train_mode, final_res=128, filters=256):
@@ -232,12 +291,12 @@ def translator(ctx, x, train_mode, final_res=128, filters=256):
         x = ctx.cbr(x, s + "conv_%d_0" % conv_id, s + "b_norm_%d_0" % conv_id, train_mode)
         x = ctx.cbr(x, s + "conv_%d_1" % conv_id, s + "b_norm_%d_1" % conv_id, train_mode)
         if size == final_res:
-            crude = ctx.conv(x, s + "conv_%d_0" % (conv_id + 1))
-            mask = torch.sigmoid(ctx.conv(x, s + "conv_%d_1" % (conv_id + 1)))
+            crude = ctx.s(s + "conv_%d_0" % (conv_id + 1), ctx.q.g(ctx.conv(x, s + "conv_%d_0" % (conv_id + 1))))
+            mask = ctx.s(s + "conv_%d_1:sigmoid" % (conv_id + 1), torch.sigmoid(ctx.q.g(ctx.conv(x, s + "conv_%d_1" % (conv_id + 1)))))
             break
         x = ctx.cbr(x, s + "conv_%d_0" % (conv_id + 1), s + "b_norm_%d_0" % (conv_id + 1), train_mode)
-        x = ctx.cbr(x, s + "conv_%d_1" % (conv_id + 1), s + "b_norm_%d_1" % (conv_id + 1), train_mode)
-        x = T.resize_bilinear_legacy(x, 2 * size, 2 * size)
+        x = ctx.cbr(x, s + "conv_%d_1" % (conv_id + 1), s + "b_norm_%d_1" % (conv_id + 1), train_mode, store=False)
+        x = ctx.upsample2x(x, s + "conv_%d_1" % (conv_id + 1))
         size = x.shape[1]
         conv_id += 2
         if filters >= 8:
@@ -247,10 +306,12 @@ def translator(ctx, x, train_mode, final_res=128, filters=256):
 
 def img_discr(ctx, x):
     """networks/__init__.py:141-151 -> logit [B,6,6,1] at 128x128 input."""
-    x = T.leaky_relu(ctx.conv(x, "img_discr/conv_0", stride=2, pad=1), 0.01)
+    def lrelu(t):
+        return T.leaky_relu(t, 0.01)
+    x = ctx.conv_act(ctx.q.a(x), "img_discr/conv_0", lrelu, stride=2, pad=1)
     for i in range(1, 6):
-        x = T.leaky_relu(ctx.conv(x, "img_discr/conv_%d" % i, stride=2, pad=1), 0.01)
-    return ctx.conv(x, "img_discr/D_logit", stride=1, pad=1, use_bias=False)
+        x = ctx.conv_act(x, "img_discr/conv_%d" % i, lrelu, stride=2, pad=1)
+    return ctx.s("img_discr/D_logit", ctx.q.g(ctx.conv(x, "img_discr/D_logit", stride=1, pad=1, use_bias=False)))
 
 
 def vgg19(ctx, rgb):
@@ -259,10 +320,12 @@ def vgg19(ctx, rgb):
     mean = torch.tensor(VGG_MEAN, dtype=rgb.dtype)
     bgr = torch.stack([rgb[..., 2] - mean[0], rgb[..., 1] - mean[1], rgb[..., 0] - mean[2]], dim=-1)
 
-    def cl(x, name):
-        return torch.relu(T.conv2d(x, P["vgg/%s/filter" % name], P["vgg/%s/biases" % name], 1, 0))
+    q = ctx.q
 
-    x = cl(bgr, "conv1_1"); c12 = cl(x, "conv1_2"); x = T.max_pool_2x2(c12)
+    def cl(x, name):
+        return ctx.s("vgg/" + name, q.a(torch.relu(q.g(T.conv2d(x, q.w(P["vgg/%s/filter" % name]), P["vgg/%s/biases" % name], 1, 0)))))
+
+    x = cl(q.a(bgr), "conv1_1"); c12 = cl(x, "conv1_2"); x = T.max_pool_2x2(c12)
     x = cl(x, "conv2_1"); c22 = cl(x, "conv2_2"); x = T.max_pool_2x2(c22)
     x = cl(x, "conv3_1"); x = cl(x, "conv3_2"); x = cl(x, "conv3_3"); c34 = cl(x, "conv3_4"); x = T.max_pool_2x2(c34)
     x = cl(x, "conv4_1"); x = cl(x, "conv4_2"); x = cl(x, "conv4_3"); c44 = cl(x, "conv4_4"); x = T.max_pool_2x2(c44)
@@ -278,11 +341,11 @@ def forward_pass(ctx, im, future_im, n_pts, is_training):
     emb = image_encoder(ctx, im, is_training)
     cur_pt = pose_encoder(ctx, im, n_pts, is_training)
     fut_pt = pose_encoder(ctx, future_im, n_pts, is_training)
-    cur_map = k1_torch.get_gaussian_maps(cur_pt, [32, 32])
-    fut_map = k1_torch.get_gaussian_maps(fut_pt, [32, 32])
-    joint = torch.cat([emb[-2], cur_map, fut_map], dim=-1)
+    cur_map = ctx.s("maps", k1_torch.get_gaussian_maps(cur_pt, [32, 32]))
+    fut_map = ctx.s("maps", k1_torch.get_gaussian_maps(fut_pt, [32, 32]))
+    joint = ctx.s("joint", ctx.q.a(torch.cat([emb[-2], cur_map, fut_map], dim=-1)))
     crude, mask = translator(ctx, joint, is_training)
-    final = im * mask + crude * (1 - mask)
+    final = ctx.s("final", im * mask + crude * (1 - mask))
     return {"final_output": final, "crude_output": crude, "mask": mask, "current_pt": cur_pt, "future_pt": fut_pt,
             "current_map": cur_map, "future_map": fut_map, "embedding": emb[-2]}
 

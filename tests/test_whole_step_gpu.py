@@ -1,0 +1,245 @@
+"""GPU: the backward pass of the WHOLE stage-1 step against the oracle, variable by variable.
+
+What gets gradients, for which variables, D run then G run: /root/reference/models/detector_translator_model.py:186-203
+(loss_D -> img_discr variables; loss_G -> everything else).
+
+The B200 path computes in bf16 with fp32 accumulation (north_star).  Two bf16 forward passes that differ only in
+accumulation order do not stay together: a 1-ulp rounding flip in one stored activation perturbs ~300 outputs of the
+next layer and flips a few of them, so the number of differing elements grows ~15x per layer until every element
+carries rounding noise (measured with scripts/faithful_probe.py: 3e-5 relative L2 after the first layer, 2e-3 after the
+fifth), and from there batch-statistics BN + ReLU amplify it ~1.2x per layer to 3.4e-2 at the generated frame.  ReLU /
+max-pool / L1-sign decisions then differ in a few per cent of the positions, and gradients (sums over masked positions)
+differ by tens of per cent - the same for ANY two bf16 implementations, e.g. the oracle with and without bf16 rounding
+(cosine 0.63 at translator/conv_1_0, 0.40 in pose_encoder, rel-L2 0.23-0.32 in img_discr: exactly the figures of the
+CUDA path against the exact oracle).  A plain end-to-end comparison therefore cannot tell a mis-wired tape from drift.
+
+So the backward pass is pinned with FORWARD SUBSTITUTION: the oracle runs with `precision.Bf16Faithful` (rounds where
+the CUDA path stores bf16) and every stored tensor of its forward pass is replaced by the value the CUDA path stored
+(`oracle.networks.Ctx.sub`), keeping the oracle's own autograd graph.  This does two things:
+  * forward: every layer's output is compared with the oracle's ON IDENTICAL INPUTS inside the real network (the
+    discrepancy `Ctx.s` logs before substituting), held to the 1e-2 bf16 conv tolerance of north_star;
+  * backward: all mask decisions and BN statistics are those of the CUDA forward, the backward is linear, and every
+    variable's gradient must match the oracle's autograd - a wrong skip-concat slice, a missing accumulation over the
+    two calls of the shared pose_encoder, a wrong max-pool / ReLU / leaky mask, a lost two-consumer gradient
+    (generated frame -> VGG and img_discr), a wrong K1 backward or a wrong image_prep adjoint shows up as a cosine
+    far from 1.
+
+A second test runs smooth fixture images against the EXACT oracle without substitution and records what bf16 costs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"paths": {"data_dir": "", "vggnet": None, "log_dir": "/tmp/kp_b200_test"},
+       "training": {"batch_size": 2, "lr": {"start_val": 1e-4, "step": 20000, "decay": 0.95}},
+       "model": {"n_pts": 40, "n_action": 9, "cell_info": [1024, 1024], "vae_dim": 64}}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cmp(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    na, nb = float(a.norm()), float(b.norm())
+    return {"cos": float(torch.dot(a, b) / (na * nb + 1e-300)), "rel_l2": float((a - b).norm() / (nb + 1e-300)), "ref_norm": nb}
+
+
+def _noise(B, seed=0):
+    rng = np.random.default_rng(seed)
+    return [torch.from_numpy(rng.uniform(-1, 1, (B, 128, 128, 3)).astype(np.float32)) for _ in range(2)]
+
+
+def _smooth(B):
+    from test_oracle_golden import S
+    im, fut = [torch.from_numpy(a.astype(np.float32)) for a in S["stage1_inputs"]()]
+    reps = -(-B // im.shape[0])
+    return im.repeat(reps, 1, 1, 1)[:B].contiguous(), fut.repeat(reps, 1, 1, 1)[:B].flip(0).contiguous()
+
+
+def _params():
+    from oracle import networks as ON
+    P = ON.init_params(0, dtype=torch.float32, bias_scale=0.02)
+    return ON.randomize_bn(P, 1)
+
+
+def _cuda_grads(model, im, fut, which, trace=None):
+    """Gradients of one run exactly as train_step computes them, without the optimiser step.  `trace`: list that
+    receives every stored tensor of the forward pass in call order (engine.Context.trace)."""
+    from kp_b200 import engine as E
+    ctx = model.ctx
+    dev = model.device
+    im, fut = im.to(dev), fut.to(dev)
+    ctx.begin_run()
+    ctx.trace = trace
+    if which == "G":
+        ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = E.Tape(), False, True, False
+        ctx.G.grad.zero_()
+        fake = model._define_forward_pass(im, fut, for_G_run=True)
+        loss = model._compute_loss_G(fake, fut, backward=True)
+        ctx.tape.backward()
+        grp = ctx.G
+    else:
+        ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = None, False, False, False
+        fake = model._define_forward_pass(im, fut, for_G_run=False)
+        ctx.tape, ctx.train_D = E.Tape(), True
+        ctx.D.grad.zero_()
+        loss = model._compute_loss_D(fake, fut, backward=True)
+        ctx.tape.backward()
+        grp = ctx.D
+    ctx.tape, ctx.train_G, ctx.train_D = None, False, False
+    ctx.trace = None
+    torch.cuda.synchronize()
+    return {n: grp.g(n).detach().cpu().clone() for n in grp.names()}, float(loss.sum().item())
+
+
+def _substitutions(trace, which, B):
+    """engine trace -> oracle substitution lists.  The two implementations batch differently: the CUDA path runs VGG on
+    gt and on pred separately (oracle: one call on [gt; pred]) and, in the D run, img_discr once on [real; fake]
+    (oracle: two calls)."""
+    sub = {}
+
+    def add(name, t):
+        sub.setdefault(name, []).append(t.detach().double().cpu())
+    for e in trace:
+        sc = e["scope"]
+        if e["kind"] == "bn":
+            add(sc + ":pre", e["y_pre"]); add(sc + ":mean", e["mean"]); add(sc + ":rstd", e["rstd"]); add(sc, e["out"])
+        elif e["kind"] == "k1":
+            add("mu", e["mu"]); add("maps", e["maps"])
+        elif sc == "translator/conv_6_0":
+            add(sc, e["out"][..., :3]); add("translator/conv_6_1:sigmoid", e["out"][..., 3:4])
+        else:
+            add(sc, e["out"])
+    for name in list(sub):
+        if name.startswith("vgg/"):
+            assert len(sub[name]) == 2
+            sub[name] = [torch.cat(sub[name], dim=0)]
+        if name.startswith("img_discr/") and which == "D":
+            assert len(sub[name]) == 1 and sub[name][0].shape[0] == 2 * B
+            sub[name] = [sub[name][0][:B], sub[name][0][B:]]
+    return sub
+
+
+def _oracle_grads(P, im, fut, which, q, sub=None, info=None):
+    from oracle import networks as ON
+    want = (lambda k: "img_discr" in k) if which == "D" else \
+        (lambda k: not k.startswith("vgg") and "moving" not in k and "img_discr" not in k)
+    Pd = {k: v.double().clone().requires_grad_(want(k)) for k, v in P.items()}
+    octx = ON.Ctx(Pd, q=q, sub=sub)
+    if info is not None:
+        info["ctx"] = octx
+    im, fut = im.double(), fut.double()
+    if which == "G":
+        ref = ON.forward_pass(octx, im, fut, 40, True)
+        loss = ON.loss_G(octx, ref["final_output"], fut)[0]
+    else:
+        with torch.no_grad():
+            ref = ON.forward_pass(octx, im, fut, 40, True)
+        loss = ON.loss_D(octx, ref["final_output"], fut)[0]
+    loss.backward()
+    # variables the loss does not depend on (image_encoder conv_7/conv_8 and their BN) have no gradient: exact zeros
+    return {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pd.items() if v.requires_grad}, float(loss)
+
+
+def _table(got, ref):
+    rows = {}
+    for n, g in got.items():
+        r = ref.get(n)
+        rows[n] = "no reference gradient" if r is None else _cmp(g, r)
+    return rows
+
+
+def _dump(tag, rows, extra):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "whole_step_%s.json" % tag), "w") as fh:
+        json.dump({"summary": extra, "variables": rows}, fh, indent=1)
+
+
+# Variables whose TRUE gradient is zero (softmax over the map is shift invariant, so the bias of the 1x1 head has none;
+# batch-statistics BN removes the preceding conv bias): what is left on both sides is rounding noise, not compared.
+def _zero_true_grad(name, rows):
+    if name == "pose_encoder/conv_0/conv2d/bias":
+        return True
+    if name.endswith("/conv2d/bias") and not name.startswith("img_discr") and not name.startswith("translator/conv_6_"):
+        return True
+    return False
+
+
+@pytest.mark.parametrize("which", ["G", "D"])
+def test_whole_step_backward_matches_oracle_with_forward_substitution(cuda_dev, which):
+    from kp_b200 import models
+    from oracle import precision
+    B = 2
+    P = _params()
+    im, fut = _noise(B)
+    model = models.DetectorTranslatorModel(CFG, is_training=True, device=cuda_dev)
+    model.ctx.load_state_dict(P)
+    model.build({"image": im.to(cuda_dev), "future_image": fut.to(cuda_dev)})
+    trace = []
+    got, loss = _cuda_grads(model, im, fut, which, trace=trace)
+    sub = _substitutions(trace, which, B)
+    info = {}
+    ref, rloss = _oracle_grads(P, im, fut, which, precision.Bf16Faithful(), sub=sub, info=info)
+    left = {k: len(v) for k, v in sub.items() if v}
+    assert not left, "stored tensors of the CUDA forward the oracle never asked for: %r" % left
+
+    # ---- forward: every stored tensor against the oracle's value computed from IDENTICAL (substituted) inputs ----
+    fwd = {}
+    for name, errs in info["ctx"].sub_err.items():
+        fwd[name] = {"rel_l2": max(e[0] for e in errs), "max_abs": max(e[1] for e in errs), "scale": max(e[2] for e in errs),
+                     "calls": len(errs)}
+    worst_fwd = max(fwd.items(), key=lambda kv: kv[1]["rel_l2"])
+
+    # ---- backward: every variable ----
+    rows = _table(got, ref)
+    checked = {n: r for n, r in rows.items() if isinstance(r, dict) and not _zero_true_grad(n, rows) and r["ref_norm"] > 0.0}
+    worst = min(checked.items(), key=lambda kv: kv[1]["cos"])
+    summary = {"run": which, "batch": B, "loss": loss, "loss_oracle": rloss, "variables": len(rows), "checked": len(checked),
+               "stored_tensors_checked": sum(v["calls"] for v in fwd.values()),
+               "worst_forward": [worst_fwd[0], worst_fwd[1]], "worst_gradient": [worst[0], worst[1]],
+               "median_cos": sorted(r["cos"] for r in checked.values())[len(checked) // 2]}
+    _dump("%s_substituted" % which, {"forward": fwd, "gradients": rows}, summary)
+    print(json.dumps(summary))
+    assert abs(loss - rloss) <= 1e-3 * abs(rloss), summary
+    bad_fwd = {n: v for n, v in fwd.items() if not v["rel_l2"] <= 1e-2}
+    assert not bad_fwd, "forward, identical inputs, above the 1e-2 bf16 tolerance: %r" % bad_fwd
+    missing = [n for n, r in rows.items() if not isinstance(r, dict)]
+    assert not missing, "variables without a reference gradient: %r" % missing
+    # no dead variable gets a gradient (image_encoder conv_7/conv_8: TF prunes them)
+    for n, r in rows.items():
+        if r["ref_norm"] == 0.0:
+            assert float(got[n].abs().max()) == 0.0, "%s: reference gradient is exactly zero, got %g" % (n, float(got[n].abs().max()))
+    bad = {n: r for n, r in checked.items() if not (r["cos"] >= 0.999 and r["rel_l2"] <= 5e-2)}
+    assert not bad, "gradient mismatch (cos < 0.999 or rel L2 > 5e-2): %r" % bad
+
+
+def test_whole_step_gradients_smooth_images_vs_exact_oracle(cuda_dev):
+    """Fixture images (smooth), exact float64 oracle, NO substitution: what bf16 arithmetic costs end to end on this
+    random-init network.  Recorded (gpurun_out/whole_step_*_smooth_exact.json -> profiles/), bounded loosely: measured
+    G-run median cosine 0.75 / D-run 0.945, the same as the oracle's own bf16-vs-exact figures (module docstring)."""
+    from kp_b200 import models
+    from oracle import precision
+    B = 2
+    P = _params()
+    im, fut = _smooth(B)
+    model = models.DetectorTranslatorModel(CFG, is_training=True, device=cuda_dev)
+    model.ctx.load_state_dict(P)
+    model.build({"image": im.to(cuda_dev), "future_image": fut.to(cuda_dev)})
+    out = {}
+    for which in ("G", "D"):
+        got, loss = _cuda_grads(model, im, fut, which)
+        ref, rloss = _oracle_grads(P, im, fut, which, precision.Exact())
+        rows = _table(got, ref)
+        checked = {n: r for n, r in rows.items() if isinstance(r, dict) and not _zero_true_grad(n, rows) and r["ref_norm"] > 0}
+        cos = sorted(r["cos"] for r in checked.values())
+        out[which] = {"loss": loss, "loss_oracle": rloss, "min_cos": cos[0], "median_cos": cos[len(cos) // 2],
+                      "frac_cos_ge_0.99": sum(c >= 0.99 for c in cos) / len(cos)}
+        _dump("%s_smooth_exact" % which, rows, out[which])
+    print(json.dumps(out))
+    assert abs(out["G"]["loss"] - out["G"]["loss_oracle"]) <= 5e-2 * abs(out["G"]["loss_oracle"])
+    assert abs(out["D"]["loss"] - out["D"]["loss_oracle"]) <= 5e-3 * abs(out["D"]["loss_oracle"])
+    assert out["D"]["min_cos"] >= 0.85 and out["G"]["median_cos"] >= 0.5, out

@@ -113,6 +113,7 @@ class Context:
         self.train_D = False                          # accumulate img_discr weight gradients
         self.train_G = False
         self.debug = None                             # dict: layer scope -> internals (tests / probes only)
+        self.trace = None                             # list of dicts, one per stored tensor in call order (tests only)
         self.zpool = None
         self.zoff = 0
         self._plans = {}
@@ -234,6 +235,13 @@ def _conv_weights(ctx, wnames, wshape=None):
     return torch.cat([ctx.p(n) for n in wnames], dim=3)
 
 
+def _scope_of(wname):
+    for suffix in ("/conv2d/kernel", "/filter"):
+        if wname.endswith(suffix):
+            return wname[:-len(suffix)]
+    return wname
+
+
 def _bias_vec(ctx, bnames, rows_pad):
     if bnames is None:
         return None
@@ -297,6 +305,8 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
                                                            N * Ho * Wo, mm, mv, relu=True, upsample=upsample)
         if ctx.debug is not None:
             ctx.debug[wnames[0].replace("/conv2d/kernel", "")] = (out, y_pre, scale, shift, mean, rstd, upsample)
+        if ctx.trace is not None:
+            ctx.trace.append(dict(scope=_scope_of(wnames[0]), kind="bn", out=out, y_pre=y_pre, mean=mean, rstd=rstd))
         if ctx.tape is not None:
             tape = ctx.tape
 
@@ -317,6 +327,8 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
     # plain conv + bias + activation in the epilogue
     y = torch.empty((N, Ho, Wo, cout), device=dev, dtype=F32 if out_f32 else BF16)
     cv.run_plan(fplan, srcs, wp, bias, y, act=act, alpha=alpha)
+    if ctx.trace is not None:
+        ctx.trace.append(dict(scope=_scope_of(wnames[0]), kind="plain", out=y))
     if ctx.tape is not None:
         tape = ctx.tape
 

@@ -177,6 +177,8 @@ def _keypoints(ctx, logits, map_hw):
     """get_coord x2 + stack (+ get_gaussian_maps) in the fused K1 kernel, with its tape entry."""
     from .. import k1
     mu, px, py, maps = k1.softargmax_render_fwd(logits, map_hw, want_prob=True)
+    if ctx.trace is not None:
+        ctx.trace.append(dict(scope="k1", kind="k1", mu=mu, maps=maps))
     if ctx.tape is not None:
         tape = ctx.tape
         H, W = logits.shape[1], logits.shape[2]
@@ -211,6 +213,8 @@ def joint_embedding(embedding, cur_map, fut_map):
     ctx = get_context()
     ctot = embedding.shape[-1] + cur_map.shape[-1] + fut_map.shape[-1]
     joint = ops.pack_channels([embedding, cur_map, fut_map], tc.round_up(ctot, 64))
+    if ctx.trace is not None:
+        ctx.trace.append(dict(scope="joint", kind="joint", out=joint[..., :ctot]))
     if ctx.tape is not None:
         tape = ctx.tape
 
@@ -258,6 +262,8 @@ def compose(im, heads, clip=False, want_parts=False):
     """final_output = im*mask + crude*(1-mask) (detector_translator_model.py:174; final_model.py:96-99 with clip)."""
     ctx = get_context()
     final, crude, mask = ops.compose_fwd(heads, im, clip=clip, want_parts=want_parts)
+    if ctx.trace is not None:
+        ctx.trace.append(dict(scope="final", kind="final", out=final))
     if ctx.tape is not None:
         tape = ctx.tape
 
