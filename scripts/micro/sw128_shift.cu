@@ -30,7 +30,7 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 
 struct Params {
     CUtensorMap mapA, mapB;
-    int P, HH, dh, dw, bo_mode, N;
+    int P, HH, dh, dw, bo_mode, N, CB;
     uint32_t a_bytes, b_bytes;
     float* out;   // [128][N]
 };
@@ -63,12 +63,13 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __grid_constant__ P
         mbar_wait(&bar[0], 0);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, p.N, 0, 0);
-        const uint32_t start = a_smem + (uint32_t)((p.dh * p.P + p.dw) * 128);
-        uint64_t a_hi = umma_smem_desc(0u, (uint32_t)p.P * 128u, 16, 2u);
+        const uint32_t RB = (uint32_t)p.CB * 2u;
+        const uint32_t lay = p.CB == 64 ? 2u : p.CB == 32 ? 4u : 6u;
+        const uint32_t start = a_smem + (uint32_t)(p.dh * p.P + p.dw) * RB;
+        uint64_t a_hi = umma_smem_desc(0u, (uint32_t)p.P * RB, 16, lay);
         if (p.bo_mode == 1) a_hi |= (uint64_t)((start >> 7) & 7u) << 49;
-        const uint64_t b_hi = umma_smem_desc(0u, 1024, 16, 2u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
+        const uint64_t b_hi = umma_smem_desc(0u, 8u * RB, 16, lay);
+        for (int k = 0; k < p.CB / 16; ++k)
             umma_bf16_if(leader, tmem, a_hi | (uint64_t)(((start + 32u * k) >> 4) & 0x3FFF), b_hi | (uint64_t)(((b_smem + 32u * k) >> 4) & 0x3FFF),
                          idesc, k == 0 ? 0u : 1u);
         umma_commit_if(leader, &bar[1]);
@@ -101,7 +102,8 @@ int main() {
         return 1;
     }
     EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(ptr);
-    const int IH = 16, IW = 8, C = 64, N = 64;   // the image IS one 8x16 output tile; halo pixels outside are zero padding
+  for (int C : {64, 32, 16}) {
+    const int IH = 16, IW = 8, N = 64;   // the image IS one 8x16 output tile; halo pixels outside are zero padding
     std::vector<__nv_bfloat16> hx(IH * IW * C), hw(N * C);
     std::vector<float> fx(IH * IW * C), fw(N * C);
     srand(1);
@@ -123,22 +125,23 @@ int main() {
         {
             cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)IW, (cuuint64_t)IH};
             cuuint64_t gstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)IW * C * 2};
-            cuuint32_t box[3] = {64u, (cuuint32_t)P, (cuuint32_t)HH};
+            cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)P, (cuuint32_t)HH};
+            const CUtensorMapSwizzle swz = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
             cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = encode(&p.mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { printf("encode A failed %d (P=%d)\n", (int)r, P); continue; }
             cuuint64_t gd2[2] = {(cuuint64_t)C, (cuuint64_t)N};
             cuuint64_t gs2[1] = {(cuuint64_t)C * 2};
-            cuuint32_t bx2[2] = {64u, (cuuint32_t)N};
+            cuuint32_t bx2[2] = {(cuuint32_t)C, (cuuint32_t)N};
             cuuint32_t es2[2] = {1, 1};
             r = encode(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dwt, gd2, gs2, bx2, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { printf("encode B failed %d\n", (int)r); continue; }
         }
-        p.P = P; p.HH = HH; p.N = N;
-        p.a_bytes = (uint32_t)(P * HH * 128);
-        p.b_bytes = (uint32_t)(N * 128);
+        p.P = P; p.HH = HH; p.N = N; p.CB = C;
+        p.a_bytes = (uint32_t)(P * HH * C * 2);
+        p.b_bytes = (uint32_t)(N * C * 2);
         p.out = dout;
         for (int bo = 0; bo < 2; ++bo) {
             for (int dh = 0; dh < 3; ++dh) {
@@ -164,13 +167,15 @@ int main() {
                                 if (d > maxd) maxd = d;
                                 if (d > 1e-3) ++bad;
                             }
-                    printf("P=%2d base_offset_mode=%d tap(dh=%d,dw=%d): max|diff| = %g, mismatches %d/%d %s\n", P, bo, dh, dw, maxd, bad,
+                    printf("CB=%d P=%2d base_offset_mode=%d tap(dh=%d,dw=%d): max|diff| = %g, mismatches %d/%d %s\n", C, P, bo, dh, dw, maxd, bad,
                            128 * N, bad ? "WRONG" : "ok");
                     bad_total += bad ? 1 : 0;
                 }
             }
         }
     }
-    printf("wrong variants: %d\n", bad_total);
+    cudaFree(dx); cudaFree(dwt); cudaFree(dout);
+    printf("CB=%d wrong variants: %d\n", C, bad_total);
+  }
     return 0;
 }

@@ -58,6 +58,11 @@ CONV_BN_CASES = [
     (2, 32, 32, [32], 3, 2, 64, False),
     (1, 32, 32, [16], 7, 1, 32, False),
     (3, 8, 8, [128], 3, 1, 128, True),
+    # output extent not a multiple of the pixel tile (20x20 -> 4x32 tiles): rows outside the image still see real input
+    # through their taps and must stay out of the batch statistics (conv_tc.cu epilogue)
+    (2, 20, 20, [32], 3, 1, 32, False),
+    (2, 20, 20, [16], 3, 1, 16, False),
+    (3, 12, 20, [64], 3, 2, 64, False),
 ]
 
 
@@ -157,6 +162,71 @@ def test_conv_bias_act_layer_forward_backward(cuda_dev, act, cout, out_f32):
     _close(ctx.G.g("t/conv2d/kernel"), w64.grad, 1e-2, "dW")
     _close(ctx.G.g("t/conv2d/bias"), b64.grad, 1e-2, "dbias")
     _close(ctx.tape.grad(xd), x64.grad, 1.5e-2, "dX")
+
+
+# Shapes of the stage-1 graph at BASELINE sizes, where the launch heuristics take other branches than at toy sizes
+# (pixel-tile choice, channel-tile halving for under-filled launches, split-K, halo kernel, parity views of stride 2):
+#   (N, H, W, C_stored, C_real, k, stride, pad, cout, act, out_f32, bias)
+SHAPE_CASES = [
+    # img_discr: 4x4 s2 with explicit pad 1 + SAME -> pads (2,2)/(2,3); odd (65) and even (34) input classes
+    (4, 128, 128, 16, 3, 4, 2, 1, 64, "leaky", False, True),       # conv_0: 128 -> 65
+    (4, 65, 65, 64, 64, 4, 2, 1, 128, "leaky", False, True),       # conv_1: 65 -> 34, pad (2,3)
+    (4, 34, 34, 128, 128, 4, 2, 1, 256, "leaky", False, True),     # conv_2: 34 -> 18
+    (8, 10, 10, 512, 512, 4, 2, 1, 1024, "leaky", False, True),    # conv_4: 10 -> 6 (few tiles, long K)
+    (64, 4, 4, 2048, 2048, 3, 1, 1, 1, "none", True, False),       # D_logit on [real; fake]: split-K path
+    # BASELINE batch: 32 images at 128x128
+    (32, 128, 128, 16, 16, 3, 1, 0, 16, "relu", False, True),      # pose_encoder conv_7_1 geometry (halo kernel)
+    (32, 128, 128, 64, 64, 3, 1, 0, 64, "relu", False, True),      # VGG conv1_2 / translator conv_5_1 geometry
+    (64, 8, 8, 512, 512, 3, 1, 0, 512, "relu", False, True),       # VGG conv5_x on 64 images: channel-tile halving
+    (32, 32, 32, 256, 208, 3, 1, 0, 256, "relu", False, True),     # translator conv_1_0: 208 real of 256 stored channels
+    (32, 128, 128, 16, 16, 1, 1, 0, 40, "none", True, True),       # 1x1 head, fp32 logits
+]
+
+
+@pytest.mark.parametrize("case", SHAPE_CASES, ids=lambda c: "N%d_%dx%d_C%d_k%ds%dp%d_to%d" % (c[0], c[1], c[2], c[4], c[5], c[6], c[7], c[8]))
+def test_conv_layer_at_graph_shapes(cuda_dev, case):
+    """Forward, data gradient, weight gradient and bias gradient of one convolution at the shapes the stage-1 graph runs
+    at BASELINE batch (reference geometry: models/networks/__init__.py:141-151 for img_discr, :75-102 translator,
+    vgg.py:13-43).  Oracle: torch CPU float32 autograd of tf_ops.conv2d on the same bf16-rounded operands."""
+    from kp_b200 import engine as E, tapconv as tc
+    N, H, W, Cst, Cre, k, stride, pad, cout, act, out_f32, use_bias = case
+    rng = np.random.default_rng(N * 1000 + H + cout)
+    x = torch.zeros((N, H, W, Cst), dtype=torch.float32)
+    x[..., :Cre] = torch.from_numpy(rng.normal(size=(N, H, W, Cre)).astype(np.float32))
+    x = x.to(BF)
+    w = torch.from_numpy((rng.normal(size=(k, k, Cre, cout)) / np.sqrt(k * k * Cre)).astype(np.float32)).to(BF).float()
+    b = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32))
+    specs = {"t/conv2d/kernel": w}
+    if use_bias:
+        specs["t/conv2d/bias"] = b
+    ctx = _mk_ctx(cuda_dev, specs)
+    ctx.tape, ctx.train_G = E.Tape(), True
+    code = {"relu": tc.ACT_RELU, "leaky": tc.ACT_LEAKY, "none": tc.ACT_NONE}[act]
+    xd = x.to(cuda_dev)
+    y = E.conv_layer(ctx, [xd], "t/conv2d/kernel", "t/conv2d/bias" if use_bias else None, k, stride, pad, act=code, alpha=0.01,
+                     out_f32=out_f32)
+    x32 = x[..., :Cre].float().requires_grad_(True)
+    w32 = w.clone().requires_grad_(True)
+    b32 = b.clone().requires_grad_(True)
+    pre = T.conv2d(x32, w32, b32 if use_bias else None, stride, pad)
+    ref = torch.relu(pre) if act == "relu" else T.leaky_relu(pre, 0.01) if act == "leaky" else pre
+    assert tuple(y.shape) == tuple(ref.shape)
+    _close(y, ref.detach(), 2e-3 if out_f32 else 1e-2, "forward")
+    cpad = -(-cout // 8) * 8
+    dout = torch.from_numpy(rng.normal(size=tuple(ref.shape)).astype(np.float32)).to(BF)
+    dy = dout
+    if out_f32:
+        dy = torch.zeros(tuple(ref.shape[:3]) + (cpad,), dtype=BF)
+        dy[..., :cout] = dout
+    ctx.tape.set_grad(y, dy.to(cuda_dev))
+    ref.backward(dout.float())
+    for fn in reversed(ctx.tape.ops):
+        fn()
+    _close(ctx.G.g("t/conv2d/kernel"), w32.grad, 1e-2, "dW")
+    if use_bias:
+        _close(ctx.G.g("t/conv2d/bias"), b32.grad, 1e-2, "dbias")
+    dx = ctx.tape.grad(xd)
+    _close(dx[..., :Cre], x32.grad, 1.5e-2, "dX")
 
 
 def test_gradient_accumulation_two_consumers(cuda_dev):

@@ -548,10 +548,12 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     int grid = device_sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
     unsigned long long* trace = nullptr;
+#ifdef KP_TRACE   // debug builds only (nvcc -DKP_TRACE): the shipped library never allocates device memory
     if (getenv("KP_TAPCONV_TRACE")) {
         cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
         cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
     }
+#endif
     p.dbg = trace;
     static bool attr_done = false;
     if (!attr_done) {
@@ -562,6 +564,7 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
     if (p.halves == 2) KP_CUDA_CHECK(launch_pdl(haloconv_kernel<2>, dim3(grid), dim3(HALO_THREADS), smem, st, p));
     else KP_CUDA_CHECK(launch_pdl(haloconv_kernel<1>, dim3(grid), dim3(HALO_THREADS), smem, st, p));
     KP_LAUNCHED();
+#ifdef KP_TRACE
     if (trace != nullptr) {
         unsigned long long h[24 * 8];
         cudaStreamSynchronize(st);
@@ -578,6 +581,7 @@ int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void
         }
         cudaFree(trace);
     }
+#endif
     return KP_OK;
 }
 

@@ -246,6 +246,12 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
+                if (p.ssum != nullptr && !valid) {
+                    // an output pixel outside the image still reads real input through its taps: keep it out of the
+                    // batch-norm statistics (Wo / Ho not a multiple of the pixel tile)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
                 epi_chunk(p, v, n_off + c0, valid, pix, lane, ks, s_bias, s_stat);
             }
             if (threadIdx.x == 64) KP_TRACE(6, lt);
@@ -493,14 +499,15 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.out_off = d->out_off; p.out_sw = d->out_sw; p.out_sh = d->out_sh; p.out_sn = d->out_sn;
     p.Cout = d->Cout; p.cout_pad = d->Cout_pad; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate;
     p.bias = bias; p.ssum = ssum; p.ssq = ssq;
-    if (getenv("KP_DEBUG_NOSTORE")) p.Cout = 0;   // experiments only: epilogue drains TMEM but stores nothing
 
     const size_t smem = (size_t)stages * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024 + epi_bytes;
     unsigned long long* trace = nullptr;
+#ifdef KP_TRACE   // debug builds only (nvcc -DKP_TRACE): the shipped library never allocates device memory
     if (getenv("KP_TAPCONV_TRACE")) {
         cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
         cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
     }
+#endif
     p.dbg = trace;
     int grid = device_sm_count() * ctas_per_sm;
     if (grid > p.total_tiles * p.ksplit) grid = p.total_tiles * p.ksplit;
@@ -519,6 +526,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     else KP_LAUNCH_TAPCONV(16);
 #undef KP_LAUNCH_TAPCONV
     KP_LAUNCHED();
+#ifdef KP_TRACE
     if (trace != nullptr) {
         // debug only: synchronise, print the per-tile timeline of CTA 0 (ns relative to the first event)
         unsigned long long h[24 * 8];
@@ -536,6 +544,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
         }
         cudaFree(trace);
     }
+#endif
     return KP_OK;
 }
 

@@ -392,10 +392,12 @@ int tapconv2_launch(const kp_tapconv_desc* d, const void* const* src, const void
         attr_done = true;
     }
     unsigned long long* trace = nullptr;
+#ifdef KP_TRACE   // debug builds only (nvcc -DKP_TRACE): the shipped library never allocates device memory
     if (getenv("KP_TAPCONV_TRACE")) {
         cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
         cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
     }
+#endif
     p.dbg = trace;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
@@ -411,6 +413,7 @@ int tapconv2_launch(const kp_tapconv_desc* d, const void* const* src, const void
     cfg.numAttrs = 1;
     KP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tapconv2_kernel, p));
     KP_LAUNCHED();
+#ifdef KP_TRACE
     if (trace != nullptr) {
         unsigned long long h[24 * 8];
         cudaStreamSynchronize(st);
@@ -427,6 +430,7 @@ int tapconv2_launch(const kp_tapconv_desc* d, const void* const* src, const void
         }
         cudaFree(trace);
     }
+#endif
     return KP_OK;
 }
 

@@ -293,10 +293,12 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     KP_REQUIRE(smem <= 227u * 1024u, "kp_wgrad: shared memory %zu exceeds the SM (internal tiling error)", smem);
     dim3 grid((unsigned)(ci_blocks * p.co_blocks), (unsigned)groups, (unsigned)splits);
     unsigned long long* trace = nullptr;
+#ifdef KP_TRACE   // debug builds only (nvcc -DKP_TRACE): the shipped library never allocates device memory
     if (getenv("KP_TAPCONV_TRACE")) {
         cudaMalloc(&trace, 24 * 8 * sizeof(unsigned long long));
         cudaMemset(trace, 0, 24 * 8 * sizeof(unsigned long long));
     }
+#endif
     p.dbg = trace;
 #define KP_LAUNCH_WGRAD(CBX, CBYV)                                                                                  \
     do {                                                                                                            \
@@ -320,6 +322,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
 #undef KP_LAUNCH_WGRAD_Y
 #undef KP_LAUNCH_WGRAD
     KP_LAUNCHED();
+#ifdef KP_TRACE
     if (trace != nullptr) {
         unsigned long long h[24 * 8];
         cudaStreamSynchronize(st);
@@ -336,6 +339,7 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
         }
         cudaFree(trace);
     }
+#endif
     return KP_OK;
 }
 

@@ -128,8 +128,17 @@ class Context:
         """Call at the start of every forward(/backward) run: re-zeroes the scratch pool with a single memset."""
         if self.zpool is None:
             self.zpool = torch.zeros(self.ZPOOL_FLOATS, device=self.device, dtype=F32)
+            self.zhigh = 0
         else:
-            self.zpool[:max(self.zoff, 1)].zero_()
+            # Re-zero up to the HIGH-WATER mark of all runs so far, not just the previous run's extent: inside a captured
+            # CUDA graph this memset has a fixed length, and an eager run in between (test_step) may have used more.
+            self.zhigh = max(self.zhigh, self.zoff, 1)
+            if torch.cuda.is_current_stream_capturing():
+                self.zcaptured = self.zhigh
+            elif getattr(self, "zcaptured", None) is not None and self.zhigh > self.zcaptured:
+                # scratch beyond what the captured memset clears was dirtied: clear it now, eagerly
+                self.zpool[self.zcaptured:self.zhigh].zero_()
+            self.zpool[:self.zhigh].zero_()
         self.zoff = 0
 
     def zeros(self, n):
@@ -278,6 +287,9 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
 
     if bn is not None and not train_mode:
         # inference: fold BN (moving statistics) into the convolution, ReLU in the epilogue
+        if ctx.tape is not None:
+            raise RuntimeError("conv_layer(%s): inference-mode (folded) batch norm records no backward; gradients through "
+                               "an is_training=False stack are not supported" % bn)
         def build():
             scale = ctx.p(bn + "/gamma") * torch.rsqrt(ctx.p(bn + "/moving_variance") + 1e-5)
             b = ctx.p(bnames[0]) if bnames else torch.zeros(cout, device=dev)

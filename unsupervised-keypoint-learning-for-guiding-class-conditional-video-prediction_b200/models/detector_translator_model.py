@@ -286,6 +286,8 @@ class DetectorTranslatorModel(BaseModel):
     def train_step(self, sess=None, feed_dict=None, step=0, batch_size=None, should_write_log=False,
                    should_write_summary=False):
         start_time = time.time()
+        if not self.is_training:
+            raise RuntimeError("train_step on a model built with is_training=False (batch norm is folded: no gradients)")
         if self._graph is not None:
             im, fut = self._next_batch(feed_dict)
             self._static[0].copy_(im, non_blocking=True); self._static[1].copy_(fut, non_blocking=True)
