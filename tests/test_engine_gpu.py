@@ -507,8 +507,70 @@ def test_halo_tile_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypa
     odt = torch.float32 if out_f32 else BF
 
     def run(halo):
+        monkeypatch.setenv("KP_TAPCONV_HALO2", "0")          # this test pins the cp.async halo kernel (csrc/conv_halo.cu)
         monkeypatch.setenv("KP_TAPCONV_HALO", "1" if halo else "0")
         monkeypatch.setenv("KP_HALO_MAX_COUT", "4096")
+        out = torch.full((n, ho, wo, cout), float("nan"), device=cuda_dev, dtype=odt)
+        st = (torch.zeros(plan.rows_pad, device=cuda_dev), torch.zeros(plan.rows_pad, device=cuda_dev)) if stats else None
+        conv.run_plan(plan, srcs, wp, None if stats else bias, out, act=tc.ACT_NONE if stats else tc.ACT_RELU, stats=st)
+        torch.cuda.synchronize()
+        return out.float().cpu(), (None if st is None else (st[0].cpu(), st[1].cpu()))
+    y_halo, st_halo = run(True)
+    y_tap, st_tap = run(False)
+    ref = T.conv2d(torch.cat([x.double() for x in xs], dim=-1), w.double(), None if stats else b.double(), 1, 0)
+    if not stats:
+        ref = torch.relu(ref)
+    scale = ref.abs().max().item()
+    assert torch.isfinite(y_halo).all()
+    assert (y_halo.double() - ref).abs().max().item() <= 1e-2 * scale
+    assert (y_halo - y_tap).abs().max().item() <= 8e-3 * scale
+    if stats:
+        s_ref, q_ref = ref.sum(dim=(0, 1, 2)), (ref * ref).sum(dim=(0, 1, 2))
+        for got in (st_halo, st_tap):
+            assert (got[0][:cout].double() - s_ref).abs().max().item() <= 2e-3 * (s_ref.abs().max().item() + ref.abs().sum(dim=(0, 1, 2)).max().item() * 1e-2)
+            assert (got[1][:cout].double() - q_ref).abs().max().item() <= 2e-3 * q_ref.abs().max().item()
+
+HALO2_CASES = [
+    # (N,H,W,[C],k,cout,out_f32,stats)  - every branch of csrc/conv_halo2.cu (TMA-staged, swizzled halo)
+    (2, 32, 32, [64], 3, 64, False, False),        # 128-byte rows, halves=2, weights resident, one CTA per SM
+    (2, 32, 32, [32], 3, 32, False, True),         # 64-byte rows, two CTAs per SM, BN statistics
+    (2, 32, 32, [16], 3, 16, False, False),        # 32-byte rows
+    (2, 32, 32, [256], 3, 256, False, True),       # four slots, streamed weight stages, two channel tiles
+    (2, 16, 16, [128], 3, 384, False, False),      # halves=1, BN=128 x 3 channel tiles
+    (3, 24, 20, [16, 32], 3, 16, False, True),     # ragged H/W, virtual concat of a 32-byte and a 64-byte source
+    (2, 40, 24, [96], 3, 48, True, False),         # 64+32 channel slots of ONE source (two tensor maps), fp32 output
+    (1, 64, 64, [32], (7, 1), 32, False, False),   # 7x1 taps (W-unrolled first layer), 38-row halo, pitch 8
+    (1, 64, 64, [16], (3, 1), 64, False, False),   # 3x1 taps (VGG conv1_1 layout)
+    (2, 128, 128, [16], 3, 16, False, False),      # the detector's 128x128 16-channel layers
+    (2, 64, 64, [128], 3, 128, False, False),      # translator 64x64: streamed weights, 512 TMEM columns, one CTA per SM
+    (4, 128, 128, [64, 64], 3, 32, False, True),   # pose_encoder conv_5_0-like concat at 128x128
+]
+
+
+@pytest.mark.parametrize("case", HALO2_CASES)
+def test_tma_halo_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypatch):
+    """csrc/conv_halo2.cu: the input halo arrives by ONE swizzled TMA box per channel slot and every tap is a start-address
+    offset of the shared-memory descriptor.  Forced on for every eligible shape (KP_TAPCONV_HALO2=2) and compared with the
+    fp64 conv oracle (<= 1e-2 of max|ref|) and with the TMA-tap kernel on the same operands (<= one bf16 ulp of max|ref|)."""
+    from kp_b200 import conv, tapconv as tc
+    N, H, W, Cs, k, cout, out_f32, stats = case
+    kh, kw = (k, k) if isinstance(k, int) else k
+    rng = np.random.default_rng(N * 1000 + H + cout)
+    cin = sum(Cs)
+    xs = [torch.from_numpy(rng.normal(size=(N, H, W, C)).astype(np.float32)).to(BF) for C in Cs]
+    w = torch.from_numpy((rng.normal(size=(kh, kw, cin, cout)) / np.sqrt(kh * kw * cin)).astype(np.float32)).to(BF).float()
+    b = torch.from_numpy(rng.normal(0, 0.2, cout).astype(np.float32))
+    plan, (n, ho, wo) = tc.plan_conv_fwd([tuple(x.shape) for x in xs], k, 1, 0, cout)
+    srcs = [x.to(cuda_dev) for x in xs]
+    wp = conv.pack_weights(plan, w.to(cuda_dev))
+    bias = conv.pad_vec(b.to(cuda_dev), plan.rows_pad)
+    odt = torch.float32 if out_f32 else BF
+    from kp_b200 import _lib
+    lib = _lib.load()
+
+    def run(halo2):
+        monkeypatch.setenv("KP_TAPCONV_HALO2", "2" if halo2 else "0")
+        monkeypatch.setenv("KP_TAPCONV_HALO", "0")
         out = torch.full((n, ho, wo, cout), float("nan"), device=cuda_dev, dtype=odt)
         st = (torch.zeros(plan.rows_pad, device=cuda_dev), torch.zeros(plan.rows_pad, device=cuda_dev)) if stats else None
         conv.run_plan(plan, srcs, wp, None if stats else bias, out, act=tc.ACT_NONE if stats else tc.ACT_RELU, stats=st)

@@ -77,12 +77,15 @@ def test_stage1_model_matches_reference_fixture(cuda_dev, training):
         "loss_G_rel": abs(lG - ref_l[5]) / ref_l[5],
         "mu_max_abs": float(np.abs(model.current_keypoints.float().cpu().numpy() - ST[tag + "_mu_current"]).max()),
     }
-    # Inference folds BN into the convolution: bf16 end to end stays within the 1e-2 conv tolerance.  Training-mode BN
-    # re-normalises every layer with batch statistics of only 2 frames, which amplifies the bf16 rounding floor (0.3 % per
-    # layer) by ~1.15x per layer over the 30-layer path (scripts/layer_probe.py); the per-layer tests in
-    # test_engine_gpu.py hold every operator to 1e-2 on identical inputs, this one bounds the accumulated drift.
-    lim = ({"final_rel_l2": 0.15, "mask_max_abs": 0.25, "loss_D_rel": 5e-3, "loss_G_rel": 5e-2, "mu_max_abs": 5e-2} if training else
-           {"final_rel_l2": 1e-2, "mask_max_abs": 1e-2, "loss_D_rel": 5e-3, "loss_G_rel": 1e-2, "mu_max_abs": 2e-3})
+    # Limits = about twice what the run achieves on B200 (round 2: train final 0.106 / mask 0.109 / loss_D 2.1e-5 /
+    # loss_G 1.8e-3 / mu 2.2e-3; inference final 2.2e-3 / mask 9.2e-4 / loss_D 3.7e-6 / loss_G 8.4e-5 / mu 5.6e-5).
+    # Inference folds BN into the convolution: bf16 end to end stays far inside the 1e-2 conv tolerance and the key points
+    # inside north_star's 1e-4.  Training-mode BN re-normalises every layer with batch statistics of only 2 frames: two bf16
+    # forward passes that differ in accumulation order diverge chaotically (tests/test_whole_step_gpu.py docstring), so the
+    # end-to-end figure is bounded loosely here and every layer is held to 1e-2 ON IDENTICAL INPUTS inside the real network
+    # by test_whole_step_backward_matches_oracle_with_forward_substitution (measured <= 1.8e-4).
+    lim = ({"final_rel_l2": 0.15, "mask_max_abs": 0.2, "loss_D_rel": 1e-4, "loss_G_rel": 4e-3, "mu_max_abs": 5e-3} if training else
+           {"final_rel_l2": 5e-3, "mask_max_abs": 2e-3, "loss_D_rel": 1e-4, "loss_G_rel": 2e-4, "mu_max_abs": 1e-4})
     bad = {k: (v, lim[k]) for k, v in got.items() if not v <= lim[k]}
     assert not bad, "%s: %r (all: %r)" % (tag, bad, got)
     print(tag, got)

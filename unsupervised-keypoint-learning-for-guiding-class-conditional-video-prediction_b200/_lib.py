@@ -7,7 +7,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkp_b200.so")
+# KP_B200_LIB selects a debug variant of the SAME library (build.py --trace); there is still no fallback of any kind
+LIB_PATH = os.environ.get("KP_B200_LIB") or os.path.join(_HERE, "libkp_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "kp_b200.h")
 
 _lib = None

@@ -41,6 +41,19 @@ def _digest():
     return h.hexdigest()
 
 
+def build_trace_variant():
+    """Debug variant with -DKP_TRACE (per-tile timeline stamps, KP_TAPCONV_TRACE=1) as libkp_b200_trace.so; selected with
+    the environment variable KP_B200_LIB.  Not part of the product build."""
+    out = os.path.join(HERE, "build", "libkp_b200_trace.so")
+    objs = []
+    for src in _sources():
+        obj = os.path.join(HERE, "build", "trace_" + os.path.basename(src)[:-3] + ".o")
+        subprocess.check_call([_nvcc(), *NVCC_FLAGS, "-DKP_TRACE", "-c", src, "-o", obj])
+        objs.append(obj)
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs, "-lcudart"])
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ and link them into libkp_b200.so. Returns the library path."""
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
@@ -81,4 +94,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:
+        os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+        print(build_trace_variant())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

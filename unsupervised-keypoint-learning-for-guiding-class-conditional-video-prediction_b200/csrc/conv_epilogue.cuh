@@ -160,4 +160,65 @@ __device__ __forceinline__ void epi_chunk(const P& p, float (&v)[16], const int 
 
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path: bf16 output, complete 16-channel chunks (Cout % 16 == 0), 16-byte aligned pixels, no accumulate, no
+// split-K, activation in {none, relu, leaky}.  The general epi_chunk above decides ~20 run-time flags per chunk; each is
+// a constant-bank load + uniform compare + branch on the slow uniform datapath, measured ~800 cycles per chunk on B200
+// (ncu source page of halo2_kernel, round 2: the epilogue, not the tensor pipe, set the pace of every layer with K <=
+// 576).  Here everything is decided once per launch on the host (epi_fast_ok) and the chunk is branch-free:
+//   stats (template) -> + bias (zeros staged when absent) -> max(v, slope*v) (slope 1 / 0 / alpha) -> two 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------------
+struct EpiFast {
+    float slope;            // activation as max(v, slope*v): none 1, relu 0, leaky alpha
+    int cout_pad;
+};
+
+template <bool STATS>
+__device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const bool valid, __nv_bfloat16* __restrict__ o, const int lane,
+                                               const float* __restrict__ s_bias_c, float* __restrict__ s_stat_c, const EpiFast f) {
+    if (STATS) {
+        float sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+        const float s1 = warp_colsum16(v, lane);
+        const float s2 = warp_colsum16(sq, lane);
+        if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            atomicAdd(s_stat_c + col, s1);
+            atomicAdd(s_stat_c + f.cout_pad + col, s2);
+        }
+    }
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias_c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 b = b4[j];
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], f.slope * v[j]);
+    if (valid) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+        o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// host: does this launch qualify for the fast epilogue?
+inline bool epi_fast_ok(const kp_tapconv_desc* d, const void* out, int ksplit) {
+    if (d->out_f32 || d->accumulate || ksplit != 1) return false;
+    if (d->Cout != d->Cout_pad || d->Cout_pad % 16 != 0) return false;
+    if (d->act != KP_ACT_NONE && d->act != KP_ACT_RELU && d->act != KP_ACT_LEAKY) return false;
+    if (d->out_off % 8 || d->out_sw % 8 || d->out_sh % 8 || d->out_sn % 8) return false;
+    return (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+inline float epi_fast_slope(const kp_tapconv_desc* d) {
+    return d->act == KP_ACT_RELU ? 0.f : d->act == KP_ACT_LEAKY ? d->alpha : 1.f;
+}
+
 }  // namespace kp

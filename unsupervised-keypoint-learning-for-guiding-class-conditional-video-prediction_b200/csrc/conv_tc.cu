@@ -52,7 +52,7 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define KP_TRACE(slot, tileidx)                                                                   \
+#define KP_TTRACE(slot, tileidx)                                                                   \
     do {                                                                                          \
         if (p.dbg != nullptr && blockIdx.x == 0 && (tileidx) < 24) p.dbg[(tileidx) * 8 + (slot)] = gtime(); \
     } while (0)
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
             int ltp = 0;
             for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++ltp) {
                 const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
-                KP_TRACE(0, ltp);
+                KP_TTRACE(0, ltp);
                 const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
                 const int w0 = (mt % p.tiles_w) * p.TW, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
                 const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                     }
                     tma_load_2d(a_dst + p.a_bytes, &p.mapB, &full[st], it0 * CB, n_off);   // [BN][64] K-major, 128B swizzle
                 }
-                KP_TRACE(1, ltp);
+                KP_TTRACE(1, ltp);
             }
         }
     } else if (warp == 1) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 const int acc = lt & 1;
                 if (lt >= 2) mbar_wait(&tempty[acc], ((lt >> 1) - 1) & 1);   // epilogue drained this buffer
                 tc_fence_after();
-                if (lane == 0) KP_TRACE(2, lt);
+                if (lane == 0) KP_TTRACE(2, lt);
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * p.BN);
                 uint32_t accum = 0u;
                 for (int it0 = it_begin; it0 < it_end; it0 += G, ++git) {
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                     accum = 1u;
                     umma_commit_if(leader, &empty[st]);
                 }
-                if (lane == 0) KP_TRACE(3, lt);
+                if (lane == 0) KP_TTRACE(3, lt);
                 umma_commit_if(leader, &tfull[acc]);
             }
         }
@@ -230,16 +230,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
             const bool valid = (uw < p.Wo) && (uh < p.Ho) && (n < p.N);
             const long long pix = p.out_off + (long long)n * p.out_sn + (long long)uh * p.out_sh + (long long)uw * p.out_sw;
             const int acc = lt & 1;
-            if (threadIdx.x == 64) KP_TRACE(4, lt);
+            if (threadIdx.x == 64) KP_TTRACE(4, lt);
             mbar_wait(&tfull[acc], (lt >> 1) & 1);
             tc_fence_after();
-            if (threadIdx.x == 64) KP_TRACE(5, lt);
+            if (threadIdx.x == 64) KP_TTRACE(5, lt);
             const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
                 float v[16];
                 __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-pixel predicated stores
                 tmem_ld16(t_row + (uint32_t)c0, v);
-                if (c0 == 0 && threadIdx.x == 64) KP_TRACE(7, lt);
+                if (c0 == 0 && threadIdx.x == 64) KP_TTRACE(7, lt);
                 if (c0 + 16 >= p.BN) {
                     // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
                     tc_fence_before();
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 }
                 epi_chunk(p, v, n_off + c0, valid, pix, lane, ks, s_bias, s_stat);
             }
-            if (threadIdx.x == 64) KP_TRACE(6, lt);
+            if (threadIdx.x == 64) KP_TTRACE(6, lt);
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
@@ -373,7 +373,9 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     KP_REQUIRE((ssum == nullptr) == (ssq == nullptr), "kp_tapconv: stats_sum and stats_sq go together");
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return KP_ERR_DRIVER;
-    // stride-1 multi-tap layers: halo-tile kernel (each input element is fetched once per tile instead of once per tap)
+    // stride-1 multi-tap layers: halo-tile kernels (each input element is fetched once per tile instead of once per tap);
+    // the TMA-staged one first, the cp.async gather kernel for what it does not take (8-channel slots)
+    if (halo2_eligible(d, ssum)) return halo2_launch(d, src, wpacked, bias, out, ssum, ssq, st);
     if (haloconv_eligible(d, ssum)) return haloconv_launch(d, src, wpacked, bias, out, ssum, ssq, st);
     // wide layers, experimental: CTA pairs (cta_group::2) halve the weight fill per SM
     if (tapconv2_eligible(d)) return tapconv2_launch(d, src, wpacked, bias, out, ssum, ssq, st);

@@ -41,6 +41,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 bool tapconv2_eligible(const kp_tapconv_desc* d);
 int tapconv2_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
                     float* ssum, float* ssq, cudaStream_t st);
+bool halo2_eligible(const kp_tapconv_desc* d, const float* ssum);
+int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
+                 float* ssum, float* ssq, cudaStream_t st);
 bool haloconv_eligible(const kp_tapconv_desc* d, const float* ssum);
 int haloconv_launch(const kp_tapconv_desc* d, const void* const* src, const void* wpacked, const float* bias, void* out,
                     float* ssum, float* ssq, cudaStream_t st);

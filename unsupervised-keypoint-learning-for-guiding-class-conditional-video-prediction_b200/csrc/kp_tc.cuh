@@ -99,6 +99,22 @@ __device__ __forceinline__ void umma_bf16_if(uint32_t leader, uint32_t tmem_d, u
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
         : "memory");
 }
+// Same, with both descriptors passed as (lo, hi) 32-bit halves and packed inside the asm block: in a loop where only the
+// 14-bit start-address fields change, the issuing warp then spends ONE uniform add per operand per MMA instead of the
+// 64-bit add / or chains the compiler emits for `desc_hi | (uint64_t)addr` (the uniform datapath runs at ~8 cycles per
+// dependent instruction, so every instruction between two UTCHMMA shows up in the issue rate).
+__device__ __forceinline__ void umma_bf16_if_split(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_if(uint32_t leader, uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
