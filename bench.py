@@ -15,7 +15,11 @@ Workloads
          shard of the frame list, no collective; a step = --pseudo-frames frames per GPU.
   render BASELINE.json configs[4] — evaluate-style rendering: FinalModel turns 64 first frames + 64 synthetic
          32-step keypoint trajectories per GPU into 64 x 32 frames (translator, inference BN).
-The default run measures `train` and appends the k1 roofline as `"k1": {...}` (a few extra seconds).
+  fwd8   BASELINE.json configs[0] — stage-1 detector+translator FORWARD on 8 frame pairs (train- and inference-mode BN), with the
+         CPU oracle of the same call timed beside it on the host cores.
+The default run measures `train` and, at N=1, appends the other configurations as sub-objects `"k1"`, `"fwd8"`, `"pseudo"`,
+`"render"` (short step counts, each with its own `roofline` and `e2e`), the per-layer table of the HBM-bound convolutions
+(`roofline.hbm_bound_layers`) and the CPU baseline (oracle train step at batch 32 on all host threads).
 """
 import argparse
 import json
@@ -37,6 +41,28 @@ K1_WORKLOAD = "BASELINE configs[1]: fused soft-argmax + Gaussian render, [128,12
 CONFIG = {"paths": {"data_dir": "", "vggnet": None, "log_dir": "/tmp/kp_b200_logs"},
           "training": {"batch_size": 32, "lr": {"start_val": 1e-4, "step": 20000, "decay": 0.95}},
           "model": {"n_pts": 40, "n_action": 9, "cell_info": [1024, 1024], "vae_dim": 64}}
+
+
+def train_config(world, batch=32):
+    """Static description of the train workload - identical in the CUDA arm and in the reference arm (the driver compares
+    the two `config` objects); everything run-specific lives under the top-level key "run"."""
+    return {"workload": TRAIN_WORKLOAD, "batch_per_gpu": batch, "frames_per_step_per_gpu": 4 * batch, "image_hw": [128, 128],
+            "n_pts": 40, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (activations + 51 M parameters + Adam slots, several GB) >> 126 MB L2; input batches rotate"}
+
+
+def _host_threads():
+    """All host cores for the CPU arms, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    os.environ.pop("OMP_NUM_THREADS", None)
+    os.environ.pop("MKL_NUM_THREADS", None)
+    torch.set_num_threads(n)
+    return n
 
 
 def _peaks():
@@ -182,23 +208,49 @@ class CpuTrainer:
         return float(lD.detach()), float(lG.detach())
 
 
-def cpu_train(batch, steps, warmup=1):
-    """frames/s (4*batch frames per step) of the torch-CPU oracle train step, median over `steps`."""
-    import torch
+def cpu_train(batch, steps, warmup=1, budget_s=None):
+    """frames/s (4*batch frames per step) of the torch-CPU oracle train step on all host threads, median over the timed
+    steps; stops early when `budget_s` seconds of timed work are spent (at least 2 steps when steps >= 2)."""
+    threads = _host_threads()
     tr = CpuTrainer(batch)
     for _ in range(warmup):
         tr.step()
     ts = []
-    for _ in range(steps):
+    for i in range(steps):
         t0 = time.perf_counter()
         tr.step()
         ts.append(time.perf_counter() - t0)
-    return 4 * batch / statistics.median(ts), torch.get_num_threads(), statistics.median(ts)
+        if budget_s is not None and sum(ts) >= budget_s and len(ts) >= min(2, steps):
+            break
+    return 4 * batch / statistics.median(ts), threads, statistics.median(ts), len(ts)
+
+
+def cpu_fwd8(pairs=8, reps=5):
+    """BASELINE configs[0] on the host: oracle forward (fp32, train- and inference-mode BN) of `pairs` frame pairs; median of
+    `reps` after one warm-up.  Returns {mode: seconds}, threads."""
+    import numpy as np
+    import torch
+    from oracle import networks as ON
+    threads = _host_threads()
+    P = ON.init_params(0, dtype=torch.float32)
+    rng = np.random.default_rng(0)
+    im, fut = [torch.from_numpy(rng.uniform(-1, 1, (pairs, 128, 128, 3)).astype(np.float32)) for _ in range(2)]
+    out = {}
+    with torch.no_grad():
+        for mode, train in (("train_bn", True), ("inference_bn", False)):
+            ts = []
+            for r in range(reps + 1):
+                t0 = time.perf_counter()
+                ON.forward_pass(ON.Ctx(P), im, fut, 40, train)
+                ts.append(time.perf_counter() - t0)
+            out[mode] = statistics.median(ts[1:])
+    return out, threads
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path.  TensorFlow 1.12 cannot be installed here, so this is the oracle
-    port of the same step (torch CPU, all host threads), on a bounded sample of the workload."""
+    port of the same step (torch CPU, all host threads) at the SAME configuration (batch 32); the number of timed steps is
+    bounded by a wall-clock budget so that the run ends within a few minutes.  Under torchrun only rank 0 works."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     if args.workload == "k1":
@@ -206,18 +258,20 @@ def run_reference(args):
         vals = [cpu_k1(8, workers, 1) for _ in range(max(args.warmup, 1) + min(args.steps, 10))][max(args.warmup, 1):]
         v, cores = statistics.median(vals), workers
         sample = "%d steps x %d frames (%d procs), numpy fp32 oracle of utils/model.py" % (len(vals), 8 * workers, workers)
-        metric, wl, steps, ms = "stage-1 frames/sec (fused soft-argmax + Gaussian render)", K1_WORKLOAD, len(vals), 1e3 * 8 * workers / v
+        metric, steps, ms = "stage-1 frames/sec (fused soft-argmax + Gaussian render)", len(vals), 1e3 * 8 * workers / v
+        config = {"workload": K1_WORKLOAD}
     else:
-        b = args.cpu_batch
-        steps = max(1, min(args.steps, args.cpu_steps))
-        v, cores, sec = cpu_train(b, steps, warmup=1)
-        sample = ("%d train_steps (D run + G run, fwd+bwd incl. VGG19, TF Adam) at batch %d instead of 32: torch-CPU fp32 "
-                  "oracle of the reference graph, %d threads" % (steps, b, cores))
-        metric, wl, ms = "stage-1 frames/sec (train_step: D run + G run)", TRAIN_WORKLOAD, sec * 1e3
+        b = args.batch
+        v, cores, sec, steps = cpu_train(b, max(1, args.steps), warmup=1, budget_s=args.cpu_budget)
+        sample = ("%d timed train_steps (D run + G run, fwd+bwd incl. VGG19, TF Adam) at batch %d after 1 warm-up step, %.1f s per "
+                  "step: torch-CPU fp32 oracle of the reference graph on %d threads (host has %d cores); timed steps bounded by a "
+                  "%d s budget" % (steps, b, sec, cores, os.cpu_count() or 0, args.cpu_budget))
+        metric, ms = "stage-1 frames/sec (train_step: D run + G run)", sec * 1e3
+        config = train_config(args.gpus, b)
     emit({
         "impl": "reference", "metric": metric, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": wl, "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
@@ -226,6 +280,8 @@ def run_reference(args):
 # GPU arms
 # --------------------------------------------------------------------------------------------------
 _RESULT_FD = None
+CONV_KERNELS = ("tapconv_kernel", "tapconv2_kernel", "haloconv_kernel", "halo2_kernel", "wgrad_kernel")
+RIDGE_FLOP_PER_BYTE = 247.0     # bf16 ridge of B200: below it a layer is HBM-bound
 
 
 def emit(line):
@@ -272,100 +328,220 @@ def _max_over_ranks(x, world, dev):
     return float(t.item())
 
 
-def bench_inference(args, world, rank, dev, lib, peaks):
-    """pseudo / render workloads: sharded over ranks with no collective."""
+def conv_profile(replay, tags, peaks, n_rep=2, detail_path=None):
+    """In-situ durations of the convolution kernels of a CAPTURED step: CUPTI activity records (torch.profiler) of `n_rep`
+    replays, zipped in launch order with the (kind, algorithmic FLOPs, algorithmic bytes, tag) entries that conv.TAGS
+    collected during the capture.  CUDA events cannot bracket a kernel inside a graph replay, and per-launch brackets of an
+    eager step include the host-side launch cost.  Returns the summary that goes into `roofline`."""
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(n_rep):
+            replay()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    all_us = sum(e.time_range.end - e.time_range.start for e in evs) / n_rep
+    conv = [e for e in evs if any(k in e.name for k in CONV_KERNELS)]
+    fam = {}
+    for e in conv:
+        k = next(k for k in CONV_KERNELS if k in e.name)
+        a = fam.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += e.time_range.end - e.time_range.start
+    out = {"all_kernels_ms": all_us * 1e-3, "kernels_per_step": len(evs) // n_rep,
+           "families": {k: {"launches": v[0] // n_rep, "ms": v[1] / n_rep * 1e-3} for k, v in fam.items()}}
+    conv_us = sum(v[1] for v in fam.values()) / n_rep
+    flops = sum(t[1] for t in tags)
+    out.update({"conv_launches": len(tags), "conv_flops": flops, "conv_ms": conv_us * 1e-3,
+                "conv_tflops": flops / (conv_us * 1e-6) / 1e12 if conv_us > 0 else None})
+    if len(conv) != n_rep * len(tags):
+        out["layer_table"] = "unavailable: %d conv kernels in %d replays vs %d tagged launches" % (len(conv), n_rep, len(tags))
+        return out
+    # per-layer aggregation (same signature = same row), averaged over the replays
+    rows = {}
+    for i, e in enumerate(conv):
+        kind, fl, by, tag = tags[i % len(tags)]
+        r = rows.setdefault((kind, tag), {"kind": kind, "layer": tag, "launches": 0, "us": 0.0, "flops": 0.0, "bytes": 0.0})
+        r["launches"] += 1
+        r["us"] += e.time_range.end - e.time_range.start
+        r["flops"] += fl
+        r["bytes"] += by
+    table = []
+    for r in rows.values():
+        for k in ("launches", "us", "flops", "bytes"):
+            r[k] = r[k] / n_rep
+        r["launches"] = int(round(r["launches"]))
+        r["tflops"] = r["flops"] / (r["us"] * 1e-6) / 1e12
+        r["gbs"] = r["bytes"] / (r["us"] * 1e-6) / 1e9
+        r["flop_per_byte"] = r["flops"] / max(r["bytes"], 1.0)
+        table.append(r)
+    table.sort(key=lambda r: -r["us"])
+    hbm = [r for r in table if r["flop_per_byte"] < RIDGE_FLOP_PER_BYTE]
+    ten = [r for r in table if r["flop_per_byte"] >= RIDGE_FLOP_PER_BYTE]
+
+    def agg(rs):
+        us, fl, by = sum(r["us"] for r in rs), sum(r["flops"] for r in rs), sum(r["bytes"] for r in rs)
+        return {"launches": sum(r["launches"] for r in rs), "ms": us * 1e-3, "tflops": fl / (us * 1e-6) / 1e12 if us else None,
+                "gbs": by / (us * 1e-6) / 1e9 if us else None}
+    a_h, a_t = agg(hbm), agg(ten)
+    out["tensor_bound_layers"] = dict(a_t, frac_of_tensor_peak=(a_t["tflops"] or 0) / peaks["bf16_tflops_sustained"],
+                                      note="conv launches with algorithmic intensity >= %.0f FLOP/B" % RIDGE_FLOP_PER_BYTE)
+    out["hbm_bound_layers"] = dict(a_h, frac_of_hbm_peak=(a_h["gbs"] or 0) / peaks["hbm_gbs"],
+                                   note="conv launches with algorithmic intensity < %.0f FLOP/B (algorithmic bytes = inputs + "
+                                        "outputs + packed weights, each once)" % RIDGE_FLOP_PER_BYTE,
+                                   top=[{"kind": r["kind"], "layer": r["layer"], "launches": r["launches"], "us": round(r["us"], 1),
+                                         "MB": round(r["bytes"] / 1e6, 1), "gbs": round(r["gbs"], 1),
+                                         "frac_of_hbm_peak": round(r["gbs"] / peaks["hbm_gbs"], 3),
+                                         "tflops": round(r["tflops"], 1)} for r in hbm[:12]])
+    if detail_path:
+        try:
+            os.makedirs(os.path.dirname(detail_path), exist_ok=True)
+            with open(detail_path, "w") as fh:
+                json.dump({"layers": table, "families": out["families"]}, fh, indent=1)
+            out["layer_table"] = os.path.relpath(detail_path, ROOT)
+        except OSError:
+            pass
+    return out
+
+
+def measure_inference(kind, args, world, rank, dev, lib, peaks, steps, warmup):
+    """pseudo / render / fwd8 workloads: sharded over ranks with no collective.  The step is captured
+    into a CUDA graph (as the train step is); `value` = K replays between CUDA events, `e2e` = pinned host inputs -> H2D ->
+    step -> results D2H every step, conv roofline from CUPTI durations inside the replayed graph."""
     import torch
     from kp_b200 import models, conv as cv
     cfg = json.loads(json.dumps(CONFIG))
     gen = torch.Generator(device=dev).manual_seed(77 + rank)
-    if args.workload == "pseudo":
+    extra = {}
+    if kind == "pseudo":
         F = args.pseudo_frames
         model = models.KeypointModel(cfg, device=dev)
-        frames = [torch.rand((F, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)]   # 2 x 805 MB at F=4096
-        host = [f.cpu().pin_memory() for f in frames]
-        run_dev = lambda i: model.detect(frames[i % 2])
-        run_host = lambda i: model.detect(host[i % 2].to(dev, non_blocking=True)).cpu()
+        static_in = [torch.rand((F, 128, 128, 3), device=dev, generator=gen) * 2 - 1]
+        pool = [torch.rand((F, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)]   # 2 x 805 MB at F=4096
+        step = lambda: model.detect(static_in[0])
         units, h2d, d2h = F, F * 128 * 128 * 3 * 4, F * 40 * 2 * 4
         metric = "stage-1 frames/sec (make_pseudo_labels: detector-only pass)"
         wl = ("BASELINE configs[3]: KeypointModel.detect over %d synthetic frames per GPU per step (the rank's shard of the frame "
               "list, no collective), inference-mode BN folded into the convolutions, random-init" % F)
-    else:
+        flop_unit = 3.648e9
+    elif kind == "render":
         V, T = args.render_videos, 32
         model = models.FinalModel(cfg, device=dev)
-        ims = [torch.rand((V, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)]
-        seqs = [torch.rand((V, T, 40, 2), device=dev, generator=gen) * 1.6 - 0.8 for _ in range(2)]
-        host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in zip(ims, seqs)]
+        static_in = [torch.rand((V, 128, 128, 3), device=dev, generator=gen) * 2 - 1,
+                     torch.rand((V, T, 40, 2), device=dev, generator=gen) * 1.6 - 0.8]
+        pool = [(torch.rand((V, 128, 128, 3), device=dev, generator=gen) * 2 - 1,
+                 torch.rand((V, T, 40, 2), device=dev, generator=gen) * 1.6 - 0.8) for _ in range(2)]
 
-        def run_dev(i):
-            model.build({"image": ims[i % 2], "pred_seq": seqs[i % 2]})
+        def step():
+            model.build({"image": static_in[0], "pred_seq": static_in[1]})
             return model.run(visualize=False)["pred_im_seq"]
-
-        out_host = torch.empty((V, T, 128, 128, 3), dtype=torch.float32).pin_memory()
-
-        def run_host(i):
-            a, b = host[i % 2]
-            model.build({"image": a.to(dev, non_blocking=True), "pred_seq": b.to(dev, non_blocking=True)})
-            out_host.copy_(model.run(visualize=False)["pred_im_seq"], non_blocking=True)
-            torch.cuda.synchronize()
-            return out_host
         units, h2d, d2h = V * T, V * 128 * 128 * 3 * 4 + V * T * 40 * 2 * 4, V * T * 128 * 128 * 3 * 4
         metric = "stage-1 frames/sec (evaluate-style rendering: translator over keypoint trajectories)"
         wl = ("BASELINE configs[4]: FinalModel.run on %d videos per GPU per step: image_encoder + pose_encoder on the first frame, "
               "%d-step synthetic trajectories -> Gaussian maps -> translator -> mask compose; %d frames per step, random-init"
               % (V, T, V * T))
-    for i in range(args.warmup):
-        run_dev(i)
+        flop_unit = 14.345e9
+    else:   # fwd8
+        Bp = args.fwd_pairs
+        cfg["training"]["batch_size"] = Bp
+        model = models.DetectorTranslatorModel(cfg, is_training=True, device=dev, seed=0)
+        static_in = [torch.rand((Bp, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)]
+        pool = [tuple(torch.rand((Bp, 128, 128, 3), device=dev, generator=gen) * 2 - 1 for _ in range(2)) for _ in range(2)]
+        model.build({"image": static_in[0], "future_image": static_in[1]})
+
+        def step():
+            model.ctx.begin_run()
+            model.ctx.tape, model.ctx.update_moving = None, False
+            return model._define_forward_pass(static_in[0], static_in[1], for_G_run=True)
+        units, h2d, d2h = 2 * Bp, 2 * Bp * 128 * 128 * 3 * 4, Bp * 128 * 128 * 3 * 4
+        metric = "stage-1 frames/sec (detector + translator forward, %d frame pairs)" % Bp
+        wl = ("BASELINE configs[0]: DetectorTranslatorModel._define_forward_pass on %d synthetic frame pairs (image_encoder, "
+              "pose_encoder x2, Gaussian maps, translator, mask compose), batch-statistics BN as train.py runs it, random-init" % Bp)
+        flop_unit = 23.0026e9 / 2
+    # eager warm-up (plan / packed-weight caches), then capture
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    cv.TAGS = []
+    n0 = lib.kp_launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        result = step()
+    launches_per_step = int(lib.kp_launch_count() - n0)
+    tags, cv.TAGS = cv.TAGS, None
+
+    def set_inputs(src):
+        src = src if isinstance(src, (tuple, list)) else (src,)
+        for dst, t in zip(static_in, src):
+            dst.copy_(t, non_blocking=True)
+    for i in range(warmup):
+        set_inputs(pool[i % 2])
+        graph.replay()
     _barrier(world)
     sampler = ClockSampler(dev.index or 0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = lib.kp_launch_count()
     sampler.start()
     ev0.record()
-    for i in range(args.steps):
-        run_dev(i)
+    for i in range(steps):
+        set_inputs(pool[i % 2])          # device-resident inputs rotate (L2 >> is exceeded by every set)
+        graph.replay()
     ev1.record()
     _barrier(world)
     clocks = sampler.stop()
-    launches = int(lib.kp_launch_count() - n0)
-    ms = _max_over_ranks(ev0.elapsed_time(ev1), world, dev) / args.steps
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world, dev) / steps
     value = world * units / (ms * 1e-3)
-    e2e_steps = max(3, min(args.steps, 10))
-    run_host(0)
+    # end to end through host buffers
+    host = [tuple(t.cpu().pin_memory() for t in (pp if isinstance(pp, (tuple, list)) else (pp,))) for pp in pool]
+    out_host = torch.empty(tuple(result.shape), dtype=result.dtype).pin_memory()
+    e2e_steps = max(3, min(steps, 10))
+    set_inputs(host[0]); graph.replay(); torch.cuda.synchronize()
     _barrier(world)
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        run_host(i)
+        set_inputs(host[i % 2])
+        graph.replay()
+        out_host.copy_(result, non_blocking=True)
+        torch.cuda.synchronize()
     _barrier(world)
     e2e_value = world * units * e2e_steps / _max_over_ranks(time.perf_counter() - t0, world, dev)
-    cv.PROFILE = []
-    torch.cuda._sleep(int(2e8))
-    run_dev(0)
-    torch.cuda.synchronize()
-    tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in cv.PROFILE)
-    tot_fl = sum(f for _, f, _, _, _ in cv.PROFILE)
-    n_conv = len(cv.PROFILE)
-    cv.PROFILE = None
-    if rank == 0:
-        peak = peaks["bf16_tflops_sustained"]
-        achieved = tot_fl / (tot_ms * 1e-3) / 1e12
-        emit({"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-              "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-              "data": "synthetic",
-              "config": {"workload": wl, "frames_per_step_per_gpu": units, "parallelism": "dp%d (sharded, no collective)" % world,
-                         "l2": "inputs of a step (>= 400 MB) >> 126 MB L2; two input sets alternate"},
-              "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                           "traffic": None, "peak_source": peaks["source"] + " (sustained)",
-                           "kernel": "kp::tapconv_kernel / kp::haloconv_kernel (all %d conv launches of one step, CUDA events per "
-                                     "launch)" % n_conv,
-                           "algorithmic_flops_per_step": tot_fl, "conv_ms": tot_ms,
-                           "whole_step_tflops": tot_fl / (ms * 1e-3) / 1e12},
-              "cpu_baseline": None,
-              "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                      "steps": e2e_steps, "note": "pinned host inputs -> H2D -> model -> results D2H, every step"},
-              "gpu_launches": launches, "clocks": clocks})
-    if world > 1:
-        torch.distributed.barrier()
-        os._exit(0)
+    prof = conv_profile(graph.replay, tags, peaks, n_rep=2,
+                        detail_path=os.path.join(ROOT, "gpurun_out", "layers_%s.json" % kind) if rank == 0 else None)
+    peak = peaks["bf16_tflops_sustained"]
+    achieved = prof.get("conv_tflops") or 0.0
+    line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": wl, "frames_per_step_per_gpu": units, "parallelism": "dp%d (sharded, no collective)" % world,
+                       "cuda_graph": True, "l2": "inputs of a step >> 126 MB L2 (fwd8: 3 MB inputs, activations 0.5 GB); two input sets alternate"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                         "kernel": "all %d convolution launches of one step (kp::halo2_kernel / kp::tapconv_kernel): algorithmic "
+                                   "FLOPs / summed in-situ CUPTI durations of the replayed graph" % len(tags),
+                         "algorithmic_flops_per_step": prof.get("conv_flops"), "conv_ms": prof.get("conv_ms"),
+                         "whole_step_tflops": flop_unit * units / (ms * 1e-3) / 1e12,
+                         "whole_step_frac": flop_unit * units / (ms * 1e-3) / 1e12 / peak,
+                         "tensor_bound_layers": prof.get("tensor_bound_layers"), "hbm_bound_layers": prof.get("hbm_bound_layers"),
+                         "families": prof.get("families"), "all_kernels_ms": prof.get("all_kernels_ms")},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "note": "pinned host inputs -> H2D -> captured step -> results D2H, every step"},
+            "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks}
+    if kind == "fwd8" and rank == 0 and world == 1:
+        try:
+            secs, threads = cpu_fwd8(args.fwd_pairs)
+            line["cpu_baseline"] = {"value": units / secs["train_bn"], "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle forward (fp32, torch CPU) of the same %d pairs: median of 5 after 1 warm-up: "
+                                              "%.3f s train-mode BN, %.3f s inference-mode BN; %d threads, host has %d cores"
+                                              % (args.fwd_pairs, secs["train_bn"], secs["inference_bn"], threads, os.cpu_count() or 0)}
+        except Exception as e:   # reporting only
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    del graph
+    return line
 
 
 def bench_k1(args, world, rank, dev, lib):
@@ -386,19 +562,38 @@ def bench_k1(args, world, rank, dev, lib):
     ev1.record()
     _barrier(world)
     ms = _max_over_ranks(ev0.elapsed_time(ev1), world, dev) / steps
+    # end to end: pinned host logits -> H2D -> kernel -> mu + maps D2H
+    e2e = None
+    if world == 1:
+        hb = min(B, 256)
+        host = torch.randn((hb, 128, 128, 40)).pin_memory()
+        mu_h, maps_h = torch.empty((hb, 40, 2)).pin_memory(), torch.empty((hb, 32, 32, 40)).pin_memory()
+        t0 = None
+        for i in range(4):
+            if i == 1:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            mu, _, _, maps = k1.softargmax_render_fwd(host.to(dev, non_blocking=True), (32, 32), want_prob=False)
+            mu_h.copy_(mu, non_blocking=True); maps_h.copy_(maps, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e = {"value": hb * 3 / (time.perf_counter() - t0), "unit": "frames/s", "h2d_bytes_per_step": hb * 128 * 128 * 40 * 4,
+               "d2h_bytes_per_step": hb * (40 * 2 + 32 * 32 * 40) * 4, "steps": 3,
+               "note": "%d frames per step from pinned host memory; bound by the host link, not by the kernel" % hb}
     del logits
     peaks = _peaks()
     achieved = K1_BYTES_PER_FRAME * B / (ms * 1e-3) / 1e9
-    traffic = None
+    traffic, tsrc = None, None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
+        tsrc = "profiles/k1_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch)"
     return {"workload": K1_WORKLOAD, "frames_per_gpu": B, "l2": "input 2.68 GB per launch >> 126 MB L2",
             "frames_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
-            "gpu_launches": int(lib.kp_launch_count() - n0),
+            "gpu_launches": int(lib.kp_launch_count() - n0), "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tsrc,
+                         "peak_source": peaks["source"],
                          "kernel": "kp::k1_fwd_fast<5,8>", "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * B}}
 
 
@@ -410,7 +605,7 @@ def run_ours(args):
         g.build()
     _barrier(world)
     import kp_b200
-    from kp_b200 import models
+    from kp_b200 import models, conv as cv
     lib = kp_b200._lib.load()
     dev = torch.device("cuda", local_rank)
     peaks = _peaks()
@@ -422,14 +617,19 @@ def run_ours(args):
                               "unit": "frames/s", "n_gpus": world, "steps": r["steps"], "warmup": args.warmup,
                               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                               "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"], "frames_per_gpu": r["frames_per_gpu"], "l2": r["l2"]},
-                              "roofline": r["roofline"], "gpu_launches": r["gpu_launches"]})
+                              "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"]})
         if world > 1:
             torch.distributed.barrier()
             os._exit(0)
         return
 
-    if args.workload in ("pseudo", "render"):
-        bench_inference(args, world, rank, dev, lib, peaks)
+    if args.workload in ("pseudo", "render", "fwd8"):
+        line = measure_inference(args.workload, args, world, rank, dev, lib, peaks, args.steps, args.warmup)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            torch.distributed.barrier()
+            os._exit(0)
         return
 
     # ------------------------------ train workload ------------------------------
@@ -447,8 +647,12 @@ def run_ours(args):
         return pool[cursor["i"] % len(pool)]
     model.build(feed)
     launches_per_step = None
+    tags = None
     if not args.no_graph:
-        model.enable_cuda_graph(B)
+        cv.TAGS = []
+        model.enable_cuda_graph(B)      # two eager warm-up steps + the capture: the last third of the tags is the captured step
+        tags, cv.TAGS = cv.TAGS, None
+        tags = tags[len(tags) - len(tags) // 3:]
         launches_per_step = model.graph_launches                         # library kernels recorded in the captured step
     for _ in range(args.warmup):
         model.train_step()
@@ -496,97 +700,57 @@ def run_ours(args):
     e2e_value = world * frames_per_step * e2e_steps / e2e_s
     model.build(feed)
 
-    # ---- conv-kernel-only tensor throughput: one eager step with CUDA events around every conv launch ----
+    # ---- convolution kernels inside the captured step (CUPTI), every rank replays (the graph holds the all-reduces) ----
     kern = None
-    if not args.no_kernel_profile:
-        # every rank runs the eager step (it contains the gradient all-reduces); only rank 0 records and reports
-        from kp_b200 import conv as cv
-        cv.PROFILE = [] if rank == 0 else None
-        saved = model._graph
-        model._graph = None
-        # The eager step is CPU-launch bound; park the GPU behind a long spin kernel so that the whole step is queued
-        # before it starts: the events then bracket kernel execution only (no launch gaps inside the brackets).
-        torch.cuda._sleep(int(4e8))
-        model.train_step()
-        torch.cuda.synchronize()
-        model._graph = saved
-        if rank == 0 and os.environ.get("KP_BENCH_CONV_DETAIL"):
-            rows = sorted(((e0.elapsed_time(e1), kind, f, tag) for kind, f, e0, e1, tag in cv.PROFILE), reverse=True)
-            for ms_, kind, f, tag in rows[:int(os.environ.get("KP_BENCH_CONV_DETAIL_ROWS", "60"))]:
-                sys.stderr.write("conv %-6s %8.1f us %8.1f GFLOP %7.1f TFLOP/s  %s\n" % (kind, ms_ * 1e3, f / 1e9, f / (ms_ * 1e-3) / 1e12, tag))
-        if rank == 0:
-            tot_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1, _ in cv.PROFILE)
-            tot_fl = sum(f for _, f, _, _, _ in cv.PROFILE)
-            by = {}
-            for kind, f, e0, e1, _ in cv.PROFILE:
-                a = by.setdefault(kind, [0.0, 0.0, 0])
-                a[0] += f; a[1] += e0.elapsed_time(e1); a[2] += 1
-            kern = {"conv_launches": len(cv.PROFILE), "conv_flops": tot_fl, "eager_events_conv_ms": tot_ms,
-                    "eager_events_conv_tflops": tot_fl / (tot_ms * 1e-3) / 1e12,
-                    "by_kind_eager_events": {k: {"launches": v[2], "ms": v[1], "tflops": v[0] / (v[1] * 1e-3) / 1e12}
-                                             for k, v in by.items()}}
-        cv.PROFILE = None
-        # In-situ kernel durations: CUPTI activity records (torch.profiler) of replays of the CAPTURED step.  CUDA events
-        # cannot bracket a kernel inside a graph replay, and bracketing the 402 conv launches of an eager step overstates
-        # them by ~40 % (17.0 ms against 11.9 ms in the graph for the same kernels), so the roofline uses these.
+    if tags is not None and not args.no_kernel_profile:
         try:
-            from torch.profiler import profile, ProfilerActivity
-            n_rep = 2
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                for _ in range(n_rep):
-                    model.train_step()
-                torch.cuda.synchronize()
-            fam = {"tapconv_kernel": [0, 0.0], "haloconv_kernel": [0, 0.0], "wgrad_kernel": [0, 0.0]}
-            all_us = 0.0
-            for e in prof.events():
-                if e.device_type != torch.autograd.DeviceType.CUDA:
-                    continue
-                dur = e.time_range.end - e.time_range.start
-                all_us += dur
-                for k in fam:
-                    if k in e.name:
-                        fam[k][0] += 1
-                        fam[k][1] += dur
-            if rank == 0 and kern is not None:
-                conv_us = sum(v[1] for v in fam.values()) / n_rep
-                kern["graph_cupti"] = {"conv_ms": conv_us * 1e-3, "conv_tflops": kern["conv_flops"] / (conv_us * 1e-6) / 1e12,
-                                       "all_kernels_ms": all_us / n_rep * 1e-3,
-                                       "families": {k: {"launches": v[0] // n_rep, "ms": v[1] / n_rep * 1e-3} for k, v in fam.items()}}
+            kern = conv_profile(model.train_step, tags, peaks, n_rep=2,
+                                detail_path=os.path.join(ROOT, "gpurun_out", "layers_train.json") if rank == 0 else None)
         except Exception as e:   # reporting only
-            if rank == 0 and kern is not None:
-                kern["graph_cupti"] = {"error": repr(e)}
+            kern = {"error": repr(e)}
 
-    k1r = None if args.no_k1 else bench_k1(args, world, rank, dev, lib)
+    subs = {}
+    if world == 1 and not args.no_subs:
+        # the other BASELINE configurations as sub-objects (short step counts; each frees its model before the next)
+        model_graph, model._graph = model._graph, None
+        del model_graph
+        model = None
+        torch.cuda.empty_cache()
+        if not args.no_k1:
+            subs["k1"] = bench_k1(args, world, rank, dev, lib)
+        for kind, st in (("fwd8", 20), ("pseudo", 5), ("render", 5)):
+            try:
+                subs[kind] = measure_inference(kind, args, world, rank, dev, lib, peaks, st, 3)
+            except Exception as e:   # a failing sub-benchmark must not take the headline line with it
+                subs[kind] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    elif not args.no_k1:
+        subs["k1"] = bench_k1(args, world, rank, dev, lib)
 
     if rank == 0:
         step_tflops = TRAIN_GFLOP_PER_EXAMPLE * B / (ms_per_step * 1e-3) / 1e3
         peak = peaks["bf16_tflops_sustained"]
-        cupti = (kern or {}).get("graph_cupti", {})
-        achieved = cupti.get("conv_tflops") or (kern["eager_events_conv_tflops"] if kern else step_tflops)
+        achieved = (kern or {}).get("conv_tflops") or step_tflops
         cpu = None
-        try:
-            v, cores, sec = cpu_train(args.cpu_batch, 1, warmup=0)
-            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": "1 train_step at batch %d (%.1f s): torch-CPU fp32 oracle of the reference graph, %d threads, host "
-                             "has %d cores" % (args.cpu_batch, sec, cores, os.cpu_count() or 0)}
-        except Exception as e:   # reporting only
-            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        if world == 1 and not args.no_cpu:
+            try:
+                v, cores, sec, n = cpu_train(args.cpu_batch, 1, warmup=0)
+                cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                       "sample": "1 train_step at batch %d (%.1f s, the same configuration): torch-CPU fp32 oracle of the reference "
+                                 "graph, %d threads, host has %d cores" % (args.cpu_batch, sec, cores, os.cpu_count() or 0)}
+            except Exception as e:   # reporting only
+                cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         line = {
             "metric": "stage-1 frames/sec (train_step: D run + G run)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": TRAIN_WORKLOAD,
-                       "batch_per_gpu": B, "frames_per_step_per_gpu": frames_per_step, "image_hw": [128, 128], "n_pts": 40,
-                       "examples_per_s": world * B / (ms_per_step * 1e-3), "parallelism": "dp%d" % world,
-                       "cuda_graph": not args.no_graph,
-                       "l2": "per-step working set (activations + 51 M parameters + Adam slots, several GB) >> 126 MB L2; "
-                             "6 input batches rotate",
-                       "losses_last_step": losses},
+            "config": train_config(world, B),
+            "run": {"examples_per_s": world * B / (ms_per_step * 1e-3), "cuda_graph": not args.no_graph, "losses_last_step": losses},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peaks["source"] + " (sustained: kernels timed inside a long step)",
-                         "kernel": "kp::tapconv_kernel / kp::haloconv_kernel / kp::wgrad_kernel: algorithmic FLOPs of all conv launches of one "
-                                   "step / their summed in-situ durations (CUPTI activity records of replays of the captured step; "
-                                   "per-launch CUDA-event brackets of an eager step are kept in kernels.*eager_events*)",
+                         "kernel": "kp::halo2_kernel / kp::tapconv_kernel / kp::wgrad_kernel: algorithmic FLOPs of all conv launches of "
+                                   "one step / their summed in-situ durations (CUPTI activity records of replays of the captured "
+                                   "step, zipped with the per-launch tags recorded at capture)",
                          "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peak,
                          "algorithmic_flops_per_step": TRAIN_GFLOP_PER_EXAMPLE * B * 1e9, "kernels": kern},
             "cpu_baseline": cpu,
@@ -597,15 +761,15 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
         }
-        if k1r is not None:
-            line["k1"] = k1r
+        line.update(subs)
         emit(line)
     if world > 1:
         # Tear down in a safe order: drop the captured graph (it holds NCCL kernels) before the communicator goes,
         # and leave through os._exit so that no destructor can block on a peer that is already gone.
         torch.distributed.barrier()
         torch.cuda.synchronize()
-        model._graph = None
+        if model is not None:
+            model._graph = None
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
@@ -616,17 +780,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="train", choices=["train", "k1", "pseudo", "render"])
+    ap.add_argument("--workload", default="train", choices=["train", "k1", "pseudo", "render", "fwd8"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="train: pairs per GPU per run")
     ap.add_argument("--frames", type=int, default=1024, help="k1: frames per GPU per launch")
     ap.add_argument("--k1-steps", type=int, default=100)
     ap.add_argument("--pseudo-frames", type=int, default=4096, help="pseudo: frames per GPU per step")
     ap.add_argument("--render-videos", type=int, default=64, help="render: videos per GPU per step (32 frames each)")
-    ap.add_argument("--cpu-batch", type=int, default=2)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--fwd-pairs", type=int, default=8, help="fwd8: frame pairs per call")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="cpu_baseline of the CUDA arm: oracle train step at this batch")
+    ap.add_argument("--cpu-budget", type=int, default=100, help="--impl reference: seconds of timed CPU steps")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-k1", action="store_true")
+    ap.add_argument("--no-subs", action="store_true", help="skip the fwd8 / pseudo / render sub-objects")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline of the CUDA arm")
     ap.add_argument("--no-kernel-profile", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

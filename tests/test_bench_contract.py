@@ -25,5 +25,5 @@ def test_reference_arm_prints_exactly_one_json_line():
 
 def test_bench_declares_every_workload_of_the_baseline():
     src = open(os.path.join(ROOT, "bench.py")).read()
-    for wl in ("train", "k1", "pseudo", "render"):
+    for wl in ("train", "k1", "pseudo", "render", "fwd8"):
         assert '"%s"' % wl in src

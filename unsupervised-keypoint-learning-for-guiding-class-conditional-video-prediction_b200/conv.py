@@ -19,13 +19,18 @@ def _stream():
 # bench.py sets PROFILE = [] to time every conv launch with CUDA events: entries (kind, algorithmic_flops, ev0, ev1).
 # Algorithmic = real channels only: plans of layers whose sources carry zero-padded channels have flop_scale < 1.
 PROFILE = None
+# bench.py sets TAGS = [] to record (kind, algorithmic_flops, tag) of every conv launch WITHOUT events (legal inside a CUDA-graph
+# capture): the n-th entry describes the n-th convolution kernel of the captured step, whose in-situ duration comes from CUPTI.
+TAGS = None
 
 
 class _Timed:
-    def __init__(self, kind, flops, tag=""):
-        self.kind, self.flops, self.tag = kind, flops, tag
+    def __init__(self, kind, flops, tag="", nbytes=0.0):
+        self.kind, self.flops, self.tag, self.nbytes = kind, flops, tag, nbytes
 
     def __enter__(self):
+        if TAGS is not None:
+            TAGS.append((self.kind, self.flops, self.nbytes, self.tag))
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -156,8 +161,18 @@ def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None
     k_real = len(plan.taps) * sum(plan.views[first + s]["C"] for s in range(plan.n_src))
     flops = 2.0 * plan.N * plan.Ho * plan.Wo * k_real * plan.rows * getattr(plan, "flop_scale", 1.0)
     tag = "N%d %dx%d K%d(taps %d) -> %d CB%d%s" % (plan.N, plan.Ho, plan.Wo, plan.Ktot, len(plan.taps), plan.rows, plan.CB,
-                                                  " +stats" if stats is not None else "") if PROFILE is not None else ""
-    with torch.cuda.device(out.device), _Timed("dgrad" if plan.pack["mode"] == "dgrad" else "fwd", flops, tag):
+                                                  " +stats" if stats is not None else "") if (PROFILE is not None or TAGS is not None) else ""
+    nbytes = 0.0
+    if TAGS is not None:
+        # algorithmic bytes: every distinct source once, the output view once, the packed weights once
+        seen = set()
+        for s_ in srcs:
+            if s_.data_ptr() not in seen:
+                seen.add(s_.data_ptr())
+                nbytes += s_.numel() * 2.0
+        nbytes += float(plan.N * plan.Ho * plan.Wo * plan.rows) * (4.0 if out.dtype == torch.float32 else 2.0) * (2.0 if accumulate else 1.0)
+        nbytes += wpacked.numel() * 2.0
+    with torch.cuda.device(out.device), _Timed("dgrad" if plan.pack["mode"] == "dgrad" else "fwd", flops, tag, nbytes):
         _lib.call("kp_tapconv_bf16", ctypes.byref(d), ptrs, wpacked.data_ptr(),
                   None if bias is None else bias.data_ptr(), out.data_ptr(),
                   None if ssum is None else ssum.data_ptr(), None if ssq is None else ssq.data_ptr(), _stream())
@@ -174,6 +189,7 @@ def run_wgrad(plan, x, dy, dw, splits=0):
     d = plan.desc(splits)
     flops = 2.0 * plan.N * plan.Ho * plan.Wo * len(plan.taps) * plan.Cin * plan.Cout * getattr(plan, "flop_scale", 1.0)
     tag = "N%d %dx%d Cin%d Cout%d taps %d CB%d" % (plan.N, plan.Ho, plan.Wo, plan.Cin, plan.Cout, len(plan.taps), plan.CB)
-    with torch.cuda.device(dw.device), _Timed("wgrad", flops, tag):
+    nbytes = x.numel() * 2.0 + dy.numel() * 2.0 + 2.0 * 4.0 * len(plan.taps) * plan.Cin * plan.Cout
+    with torch.cuda.device(dw.device), _Timed("wgrad", flops, tag, nbytes):
         _lib.call("kp_tapconv_wgrad_bf16", ctypes.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), _stream())
     return dw

@@ -168,26 +168,45 @@ __device__ __forceinline__ void epi_chunk(const P& p, float (&v)[16], const int 
 // 576).  Here everything is decided once per launch on the host (epi_fast_ok) and the chunk is branch-free:
 //   stats (template) -> + bias (zeros staged when absent) -> max(v, slope*v) (slope 1 / 0 / alpha) -> two 16-byte stores.
 // ---------------------------------------------------------------------------------------------------------------
+
+// Per-channel sum / sum of squares of one or two 16-column chunks (the same columns of the two accumulator halves) into the
+// warp-PRIVATE shared-memory accumulators s_stat_w[0..] / s_stat_w[cout_pad..]: one transpose-reduce per statistic for both
+// halves together, then a plain read-modify-write by the 16 owning lanes (no atomics: nobody else touches this warp's copy;
+// the four copies are summed once at the end of the kernel).
+template <int NV>
+__device__ __forceinline__ void epi_stats16(const float (&v)[NV][16], const int lane, float* __restrict__ s_stat_w, const int cout_pad) {
+    float s[16], q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        s[j] = v[0][j];
+        q[j] = v[0][j] * v[0][j];
+    }
+#pragma unroll
+    for (int h = 1; h < NV; ++h) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            s[j] += v[h][j];
+            q[j] = fmaf(v[h][j], v[h][j], q[j]);
+        }
+    }
+    const float s1 = warp_colsum16(s, lane);
+    const float s2 = warp_colsum16(q, lane);
+    if ((lane & 1) == 0) {
+        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        s_stat_w[col] += s1;
+        s_stat_w[cout_pad + col] += s2;
+    }
+    __syncwarp();
+}
+
 struct EpiFast {
     float slope;            // activation as max(v, slope*v): none 1, relu 0, leaky alpha
     int cout_pad;
 };
 
-template <bool STATS>
-__device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const bool valid, __nv_bfloat16* __restrict__ o, const int lane,
-                                               const float* __restrict__ s_bias_c, float* __restrict__ s_stat_c, const EpiFast f) {
-    if (STATS) {
-        float sq[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-        const float s1 = warp_colsum16(v, lane);
-        const float s2 = warp_colsum16(sq, lane);
-        if ((lane & 1) == 0) {
-            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            atomicAdd(s_stat_c + col, s1);
-            atomicAdd(s_stat_c + f.cout_pad + col, s2);
-        }
-    }
+// bias + activation + bf16 store of one 16-column chunk of one pixel (statistics are taken before, see epi_stats16)
+__device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const bool valid, __nv_bfloat16* __restrict__ o,
+                                               const float* __restrict__ s_bias_c, const EpiFast f) {
     const float4* b4 = reinterpret_cast<const float4*>(s_bias_c);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -271,8 +271,9 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
         const int et = threadIdx.x - 128;
         for (int i = et; i < p.cout_pad; i += 128) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
         if (p.ssum != nullptr)
-            for (int i = et; i < 2 * p.cout_pad; i += 128) s_stat[i] = 0.f;
+            for (int i = et; i < 8 * p.cout_pad; i += 128) s_stat[i] = 0.f;     // four warp-private copies of [2][cout_pad]
         named_bar_sync(1, 128);
+        float* const s_stat_w = s_stat + (warp - 4) * 2 * p.cout_pad;
         if (EPI != 0) {
             // fast epilogue: everything that is constant for the launch sits in registers, the chunk is branch-free
             const EpiFast ef = {p.slope, p.cout_pad};
@@ -295,26 +296,37 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
                 mbar_wait(&tfull[acc], (lt / acc_bufs) & 1);
                 tc_fence_after();
                 if (et == 0) KP_H2TRACE(6, lt);
+                // chunk-major: the same 16 columns of both accumulator halves are in registers together, so the batch-norm
+                // statistics need ONE transpose-reduce per statistic per chunk for the whole 256-pixel tile
+                bool valid[HALVES];
+                __nv_bfloat16* o_p[HALVES];
 #pragma unroll
                 for (int hf = 0; hf < HALVES; ++hf) {
                     const int uh = h0 + hf * 16 + th;
-                    const bool valid = (uh < Ho) && (uw < Wo);
-                    __nv_bfloat16* const o_p = o_n + (long long)uh * out_sh;
-                    const uint32_t t_row = t_lane + (uint32_t)((acc * HALVES + hf) * BN);
-                    for (int c0 = 0; c0 < BN; c0 += 16) {
-                        float v[16];
-                        tmem_ld16(t_row + (uint32_t)c0, v);
-                        if (hf == HALVES - 1 && c0 + 16 >= BN) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[acc]);
-                        }
-                        if (EPI == 2 && !valid) {
+                    valid[hf] = (uh < Ho) && (uw < Wo);
+                    o_p[hf] = o_n + (long long)uh * out_sh;
+                }
+                const uint32_t t_row = t_lane + (uint32_t)(acc * HALVES * BN);
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    float v[HALVES][16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                        }
-                        epi_chunk_fast<EPI == 2>(v, valid, o_p + c0, lane, s_bias + n_off + c0, s_stat + n_off + c0, ef);
+                    for (int hf = 0; hf < HALVES; ++hf) tmem_ld16(t_row + (uint32_t)(hf * BN + c0), v[hf]);
+                    if (c0 + 16 >= BN) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
+                    if (EPI == 2) {
+#pragma unroll
+                        for (int hf = 0; hf < HALVES; ++hf)
+                            if (!valid[hf]) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[hf][j] = 0.f;
+                            }
+                        epi_stats16<HALVES>(v, lane, s_stat_w + n_off + c0, ef.cout_pad);
+                    }
+#pragma unroll
+                    for (int hf = 0; hf < HALVES; ++hf) epi_chunk_fast(v[hf], valid[hf], o_p[hf] + c0, s_bias + n_off + c0, ef);
                 }
                 if (et == 0) KP_H2TRACE(7, lt);
             }
@@ -351,7 +363,7 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
     #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = 0.f;
                         }
-                        epi_chunk(p, v, n_off + c0, valid, pix, lane, 0, s_bias, s_stat);
+                        epi_chunk(p, v, n_off + c0, valid, pix, lane, 0, s_bias, s_stat_w);
                     }
                 }
                 if (et == 0) KP_H2TRACE(7, lt);
@@ -359,9 +371,10 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
-            for (int i = et; i < p.cout_pad; i += 128) {
-                atomicAdd(p.ssum + i, s_stat[i]);
-                atomicAdd(p.ssq + i, s_stat[p.cout_pad + i]);
+            const int cp = p.cout_pad;
+            for (int i = et; i < cp; i += 128) {
+                atomicAdd(p.ssum + i, s_stat[i] + s_stat[2 * cp + i] + s_stat[4 * cp + i] + s_stat[6 * cp + i]);
+                atomicAdd(p.ssq + i, s_stat[cp + i] + s_stat[3 * cp + i] + s_stat[5 * cp + i] + s_stat[7 * cp + i]);
             }
         }
     }
@@ -510,7 +523,7 @@ int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* w
     p.a_slot_bytes = ((uint32_t)(p.R * p.pitch) * (uint32_t)max_nch * 2u + 1023u) & ~1023u;
     p.b_bytes = (uint32_t)BN * 128u;
     auto rcp32 = [](int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); };
-    const uint32_t epi_bytes = 3u * (uint32_t)d->Cout_pad * sizeof(float);
+    const uint32_t epi_bytes = (ssum != nullptr ? 9u : 1u) * (uint32_t)d->Cout_pad * sizeof(float);   // bias (+ four warp-private [2][Cout_pad] statistics)
     const uint32_t all_b = (uint32_t)(ns * d->n_taps) * p.b_bytes;
     const uint32_t fixed = epi_bytes + 1024u + 512u;
     // Two CTAs per SM whenever one CTA fits half of the SM's shared memory and TMEM: two independent TMA / issue /

@@ -40,7 +40,7 @@ struct alignas(64) TapConvKParams {
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
     int Cout, cout_pad, out_f32, act, accumulate;
-    float alpha;
+    float alpha, slope;
     const float* bias;
     float* ssum;
     float* ssq;
@@ -67,7 +67,9 @@ __device__ __forceinline__ float apply_act(float x, int act, float alpha, bool l
     }
 }
 
-template <int CB>
+// EPI: 0 = general epilogue (epi_chunk), 1 = fast epilogue (conv_epilogue.cuh: branch-free bias + activation + bf16 stores),
+// 2 = fast epilogue + batch-norm statistics.
+template <int CB, int EPI>
 __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__ TapConvKParams p) {
     constexpr uint32_t ROW_BYTES = CB * 2;
     constexpr uint32_t SBO = 8 * ROW_BYTES;
@@ -214,12 +216,51 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         // on the short-K layers) and keep the batch-norm partial sums per CTA: they are flushed with ONE global atomic
         // per channel per CTA after the last tile instead of one per channel per warp per tile.
         const int et = threadIdx.x - 64;
-        if (p.bias != nullptr)
-            for (int i = et; i < p.cout_pad; i += 128) s_bias[i] = __ldg(p.bias + i);
+        for (int i = et; i < p.cout_pad; i += 128) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
         if (p.ssum != nullptr)
-            for (int i = et; i < 2 * p.cout_pad; i += 128) s_stat[i] = 0.f;
+            for (int i = et; i < 8 * p.cout_pad; i += 128) s_stat[i] = 0.f;      // four warp-private copies of [2][cout_pad]
         named_bar_sync(1, 128);
+        float* const s_stat_w = s_stat + (warp - 2) * 2 * p.cout_pad;
         int lt = 0;
+        if (EPI != 0) {
+            // fast epilogue (ksplit == 1): launch constants in registers, branch-free chunks
+            const EpiFast ef = {p.slope, p.cout_pad};
+            __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_off;
+            const long long out_sn = p.out_sn, out_sh = p.out_sh, out_sw = p.out_sw;
+            const int Ho = p.Ho, Wo = p.Wo, N = p.N, BN = p.BN, n_tiles = p.n_tiles, tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+            const int TW = p.TW, TH = p.TH, TN = p.TN;
+            const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+            for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x, ++lt) {
+                const int mt = work / n_tiles, nt = work - mt * n_tiles;
+                const int w0 = (mt % tiles_w) * TW, h0 = ((mt / tiles_w) % tiles_h) * TH;
+                const int n0 = (mt / (tiles_w * tiles_h)) * TN;
+                const int n_off = nt * BN;
+                const int uw = w0 + tw, uh = h0 + th, n = n0 + tn;
+                const bool valid = (uw < Wo) && (uh < Ho) && (n < N);
+                __nv_bfloat16* const o_p = outp + (long long)n * out_sn + (long long)uh * out_sh + (long long)uw * out_sw + n_off;
+                const int acc = lt & 1;
+                mbar_wait(&tfull[acc], (lt >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_row = t_lane + (uint32_t)(acc * BN);
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    float v[1][16];
+                    tmem_ld16(t_row + (uint32_t)c0, v[0]);
+                    if (c0 + 16 >= BN) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    if (EPI == 2) {
+                        if (!valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[0][j] = 0.f;
+                        }
+                        epi_stats16<1>(v, lane, s_stat_w + n_off + c0, ef.cout_pad);
+                    }
+                    epi_chunk_fast(v[0], valid, o_p + c0, s_bias + n_off + c0, ef);
+                }
+            }
+        } else
         for (int work = blockIdx.x; work < p.total_tiles * p.ksplit; work += gridDim.x, ++lt) {
             const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
@@ -252,15 +293,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
-                epi_chunk(p, v, n_off + c0, valid, pix, lane, ks, s_bias, s_stat);
+                epi_chunk(p, v, n_off + c0, valid, pix, lane, ks, s_bias, s_stat_w);
             }
             if (threadIdx.x == 64) KP_TTRACE(6, lt);
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
-            for (int i = et; i < p.cout_pad; i += 128) {
-                atomicAdd(p.ssum + i, s_stat[i]);
-                atomicAdd(p.ssq + i, s_stat[p.cout_pad + i]);
+            const int cp = p.cout_pad;
+            for (int i = et; i < cp; i += 128) {
+                atomicAdd(p.ssum + i, s_stat[i] + s_stat[2 * cp + i] + s_stat[4 * cp + i] + s_stat[6 * cp + i]);
+                atomicAdd(p.ssq + i, s_stat[cp + i] + s_stat[3 * cp + i] + s_stat[5 * cp + i] + s_stat[7 * cp + i]);
             }
         }
     }
@@ -483,7 +525,7 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     // issuers; the 256-wide tiles need all 512 TMEM columns and most of the shared memory, so they run alone.
     // Short-K tiles (<= 8 K groups, narrow channel tile) are bound by the latency of the epilogue chain, not by the
     // tensor pipe: a third CTA per SM adds epilogue warps.
-    const uint32_t epi_bytes = 3u * (uint32_t)d->Cout_pad * sizeof(float);
+    const uint32_t epi_bytes = (ssum != nullptr ? 9u : 1u) * (uint32_t)d->Cout_pad * sizeof(float);   // bias (+ four warp-private [2][Cout_pad] statistics)
     int ctas_per_sm = p.tmem_cols <= 256 ? 2 : 1;
     if (p.tmem_cols <= 128 && p.groups_per_split <= 8) ctas_per_sm = 3;
     if (p.tmem_cols <= 128 && p.groups_per_split <= 1) ctas_per_sm = 4;   // one K group per tile: pure epilogue/latency work
@@ -491,7 +533,10 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
         const int want = atoi(e);
         ctas_per_sm = want >= 4 && p.tmem_cols <= 128 ? 4 : want >= 3 && p.tmem_cols <= 128 ? 3 : want >= 2 && p.tmem_cols <= 256 ? 2 : 1;
     }
-    uint32_t budget = (ctas_per_sm == 4 ? 52u : ctas_per_sm == 3 ? 70u : ctas_per_sm == 2 ? 108u : 216u) * 1024u - epi_bytes;
+    auto cta_budget = [](int c) { return (c == 4 ? 52u : c == 3 ? 70u : c == 2 ? 108u : 216u) * 1024u; };
+    while (ctas_per_sm > 1 && cta_budget(ctas_per_sm) < epi_bytes + 2u * p.stage_bytes) --ctas_per_sm;   // wide Cout: the staged bias needs room
+    KP_REQUIRE(cta_budget(ctas_per_sm) >= epi_bytes + 2u * p.stage_bytes, "kp_tapconv: tile does not fit shared memory (Cout_pad=%d)", d->Cout_pad);
+    uint32_t budget = cta_budget(ctas_per_sm) - epi_bytes;
     if (const char* e = getenv("KP_TAPCONV_SMEM_KB")) budget = (uint32_t)atoi(e) * 1024u;
     int stages = (int)(budget / p.stage_bytes);
     if (stages < 2) stages = 2;
@@ -513,19 +558,28 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     p.dbg = trace;
     int grid = device_sm_count() * ctas_per_sm;
     if (grid > p.total_tiles * p.ksplit) grid = p.total_tiles * p.ksplit;
-#define KP_LAUNCH_TAPCONV(CBV)                                                                                      \
+    const int epi = (p.ksplit == 1 && epi_fast_ok(d, out, 1)) ? (ssum != nullptr ? 2 : 1) : 0;
+    p.slope = epi_fast_slope(d);
+#define KP_LAUNCH_TAPCONV_E(CBV, E)                                                                                 \
     do {                                                                                                            \
         static bool attr_done = false;                                                                              \
         if (!attr_done) {                                                                                           \
-            KP_CUDA_CHECK(cudaFuncSetAttribute(tapconv_kernel<CBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+            KP_CUDA_CHECK(cudaFuncSetAttribute(tapconv_kernel<CBV, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                227 * 1024));                                                        \
             attr_done = true;                                                                                       \
         }                                                                                                           \
-        KP_CUDA_CHECK(launch_pdl(tapconv_kernel<CBV>, dim3(grid), dim3(192), smem, st, p));                                                            \
+        KP_CUDA_CHECK(launch_pdl(tapconv_kernel<CBV, E>, dim3(grid), dim3(192), smem, st, p));                      \
+    } while (0)
+#define KP_LAUNCH_TAPCONV(CBV)                                                                                      \
+    do {                                                                                                            \
+        if (epi == 2) KP_LAUNCH_TAPCONV_E(CBV, 2);                                                                  \
+        else if (epi == 1) KP_LAUNCH_TAPCONV_E(CBV, 1);                                                             \
+        else KP_LAUNCH_TAPCONV_E(CBV, 0);                                                                           \
     } while (0)
     if (CB == 64) KP_LAUNCH_TAPCONV(64);
     else if (CB == 32) KP_LAUNCH_TAPCONV(32);
     else KP_LAUNCH_TAPCONV(16);
+#undef KP_LAUNCH_TAPCONV_E
 #undef KP_LAUNCH_TAPCONV
     KP_LAUNCHED();
 #ifdef KP_TRACE
