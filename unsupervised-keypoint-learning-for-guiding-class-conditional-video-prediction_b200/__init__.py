@@ -13,5 +13,7 @@ from . import engine  # noqa: F401
 from .utils import model as model_utils  # noqa: F401
 from . import networks  # noqa: F401
 from . import models  # noqa: F401
+from . import checkpoint  # noqa: F401
+from . import pseudo_labels  # noqa: F401
 
-__all__ = ["model_utils", "k1", "networks", "models", "engine", "ops", "conv", "tapconv"]
+__all__ = ["model_utils", "k1", "networks", "models", "engine", "ops", "conv", "tapconv", "checkpoint", "pseudo_labels"]

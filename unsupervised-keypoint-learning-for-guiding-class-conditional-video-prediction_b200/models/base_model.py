@@ -3,7 +3,7 @@
 Same abstract interface (build / train_step / test_step / collect_test_results / initialize_loggers /
 save_checkpoint / restore).  `sess` and `feed_dict` arguments are accepted for call-site compatibility and
 ignored (there is no session: kernels are enqueued eagerly on the current CUDA stream).  Checkpoints are
-name-keyed state dicts using the TF variable names (torch.save of {name: tensor}); `restore` loads only the
+name-keyed `.npz` files using the TF variable names incl. the Adam slots (checkpoint.py); `restore` loads only the
 names present in both the file and the model, like the reference's filtered tf.train.Saver (:83-92).
 """
 import logging
@@ -60,19 +60,34 @@ class BaseModel(ABC):
         os.makedirs(osp.join(log_dir, self.__class__.name), exist_ok=True)
 
     def save_checkpoint(self, sess, step):
+        """reference :74-81 -> `<log_dir>/<name>/model.ckpt-<step>.npz` (TF variable names, see checkpoint.py).
+        Data parallel: the batch-norm moving statistics are per replica (each normalises its own shard), so they are
+        averaged over the replicas first and only rank 0 writes the file; every rank returns the path."""
+        from .. import checkpoint, dp
         name = self.__class__.name
-        path = osp.join(self.log_dir, name, 'model.ckpt-%d.pt' % int(step))
-        sd = {k: v.cpu() for k, v in self.ctx.state_dict().items()}
-        extra = getattr(self, "_extra_state", lambda: {})()
-        torch.save({"variables": sd, "extra": extra}, path)
+        path = osp.join(self.log_dir, name, 'model.ckpt-%d.npz' % int(step))
+        world = dp.world_size(getattr(self, "pg", None))
+        if world > 1 and self.ctx.S.data is not None and self.ctx.S.data.numel():
+            dp.allreduce_sum_(self.ctx.S.data, getattr(self, "pg", None))
+            self.ctx.S.data.div_(world)
+            self.ctx.params_changed()
+        if dp.rank(getattr(self, "pg", None)) == 0:
+            os.makedirs(osp.dirname(path), exist_ok=True)
+            checkpoint.save_npz(path, checkpoint.export_variables(self))
         return path
 
     def restore(self, sess, checkpoint_path):
-        blob = torch.load(checkpoint_path, map_location="cpu")
-        sd = blob["variables"] if "variables" in blob else blob
-        loaded = self.ctx.load_state_dict(sd)
+        """reference :83-92: restore by NAME, only what both the file and the model have.  `.npz` (this package, or a dump of a
+        TF checkpoint reader); `.pt` files of round 1 are read with weights_only=True."""
+        from .. import checkpoint
+        if str(checkpoint_path).endswith(".pt"):
+            blob = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+            sd = blob["variables"] if "variables" in blob else blob
+            loaded = self.ctx.load_state_dict(sd)
+            if "extra" in blob and hasattr(self, "_load_extra_state"):
+                self._load_extra_state(blob["extra"])
+        else:
+            loaded = checkpoint.import_variables(self, checkpoint.load_npz(checkpoint_path))
         print('vars-to-RESTORE:')
         print('\n'.join(loaded))
-        if "extra" in blob and hasattr(self, "_load_extra_state"):
-            self._load_extra_state(blob["extra"])
         return loaded

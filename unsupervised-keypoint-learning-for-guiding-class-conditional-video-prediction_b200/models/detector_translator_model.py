@@ -54,6 +54,11 @@ class DetectorTranslatorModel(BaseModel):
         self._side = None                  # side stream for the overlapped discriminator update (data parallel only)
         self._d_pending = False
         self.overlap_d_update = os.environ.get("KP_OVERLAP_D_UPDATE", "1") != "0"
+        # data parallel: all-reduce the generator gradients in buckets (translator / pose_encoder / image_encoder, the
+        # order in which the backward pass completes them) on the side stream, under the rest of the backward pass
+        self.overlap_g_allreduce = os.environ.get("KP_OVERLAP_G_ALLREDUCE", "1") != "0"
+        self._g_pending = False
+        self._g_done = []
         # outputs of the last forward pass (names follow the reference's attributes)
         self.final_output = self.crude_output = self.mask = None
         self.current_keypoints = self.future_keypoints = None
@@ -123,9 +128,11 @@ class DetectorTranslatorModel(BaseModel):
         tm = self.is_training
         embeddings = networks.image_encoder(im, tm) if for_G_run else \
             [im] + networks.encoder(networks._prep7(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
+        self._grad_bucket_marker("pose_encoder/")        # runs (in the backward pass) after BOTH pose_encoder calls are done
         current_gauss_pt, current_pt_map = networks.pose_encoder_with_maps(im, self.n_points, tm, (32, 32))
         future_gauss_pt, future_pt_map = networks.pose_encoder_with_maps(future_im, self.n_points, tm, (32, 32))
         joint_embedding = networks.joint_embedding(embeddings[-2], current_pt_map, future_pt_map)
+        self._grad_bucket_marker("translator/")          # ... after the translator's last weight gradient
         heads = networks.translator_heads(joint_embedding, tm)
         final_output = networks.compose(im, heads)
         self.final_output = final_output
@@ -183,6 +190,36 @@ class DetectorTranslatorModel(BaseModel):
         if self.world > 1:
             dp.allreduce_sum_(buf, self.pg)
 
+    def _bucket_range(self, prefix):
+        """[lo, hi) of the flat generator buffer holding the variables whose names start with `prefix` (contiguous: the
+        variables are declared network by network, networks.build_parameters)."""
+        G = self.ctx.G
+        offs = [(off, off + (int(torch.tensor(shape).prod()) + 3) // 4 * 4) for name, shape, off in G.specs if name.startswith(prefix)]
+        lo, hi = min(o[0] for o in offs), max(o[1] for o in offs)
+        inside = sum(1 for name, _, off in G.specs if lo <= off < hi)
+        assert inside == len(offs), "variables of %r are not contiguous in the flat buffer" % prefix
+        return lo, hi
+
+    def _grad_bucket_marker(self, prefix):
+        """Tape entry recorded BEFORE a network's forward: in the backward pass it runs right after that network's last
+        weight gradient, and starts the all-reduce of its gradient bucket on the side stream while the backward pass of the
+        networks further upstream goes on (data parallel only; joined in _run_G before Adam)."""
+        ctx = self.ctx
+        if ctx.tape is None or self.world <= 1 or not self.overlap_g_allreduce or not ctx.train_G:
+            return
+        lo, hi = self._bucket_range(prefix)
+        self._g_done.append((lo, hi))
+
+        def fire():
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._allreduce(ctx.G.grad[lo:hi])
+            self._g_pending = True
+        ctx.tape.record(fire)
+
     # ---- the two runs of one train step ----
     def _run_D(self, im, future_im):
         ctx = self.ctx
@@ -227,12 +264,26 @@ class DetectorTranslatorModel(BaseModel):
         ctx.begin_run()
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = E.Tape(), True, True, False
         ctx.G.grad.zero_()
+        self._g_done = []
         fake = self._define_forward_pass(im, future_im, for_G_run=True)
         loss = self._compute_loss_G(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.update_moving, ctx.train_G = None, False, False
         self._join_D()
-        self._allreduce(ctx.G.grad)
+        if self.world > 1:
+            # whatever the bucket markers have not sent yet (image_encoder: complete only now), then join the side stream
+            rest, pos = [], 0
+            for lo, hi in sorted(self._g_done):
+                if lo > pos:
+                    rest.append((pos, lo))
+                pos = max(pos, hi)
+            if pos < ctx.G.grad.numel():
+                rest.append((pos, ctx.G.grad.numel()))
+            for lo, hi in rest:
+                self._allreduce(ctx.G.grad[lo:hi])
+            if self._g_pending:
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._g_pending = False
         self.t_G += 1
         ops.adam_tf(ctx.G.data, ctx.G.grad, ctx.G.m, ctx.G.v, self._current_lr(), self.t_G, grad_scale=1.0 / self.world,
                     lr_t_dev=self._lr_dev[1:2] if self._lr_dev is not None else None)

@@ -48,6 +48,11 @@ class KeypointModel(BaseModel):
         pts = self.detect(im.reshape(-1, im.shape[-3], im.shape[-2], im.shape[-1]))
         return {'pts': pts.reshape(-1, T, self.n_points, 2), 'idx': b.get('idx'), 'len': b.get('len'), 'im': im}
 
+    def write_pseudo_labels(self, videos, out_dir, rank=None, world=None):
+        """make_pseudo_labels.py:83-101: one `{idx:04d}.npy` ([len, n_pts, 2] float32) per video of this rank's shard."""
+        from .. import pseudo_labels
+        return pseudo_labels.write_pseudo_labels(self.detect, videos, out_dir, rank, world)
+
     def train_step(self, sess, feed_dict, step, batch_size, should_write_log=False, should_write_summary=False):
         """This model is not trainable"""
         raise NotImplementedError
