@@ -128,10 +128,15 @@ typedef struct {
     int act; float alpha;
     int accumulate;                          /* != 0: out += result instead of out = result */
     int TW, TH, TN, BN;                      /* tile: TW*TH*TN == 128 pixels x BN channels; 0 = let the library choose */
+    int stat_groups;                         /* batch-norm statistics per batch segment: images [g*N/G, (g+1)*N/G) accumulate
+                                                into stats_sum/stats_sq + g*Cout_pad (G = stat_groups, 0/1 = one segment).  Two
+                                                calls of a shared-weight network (pose_encoder on image and future_image,
+                                                detector_translator_model.py:166-167) run as ONE launch on the concatenated batch
+                                                and still normalise each call with its own statistics.                          */
 } kp_tapconv_desc;
 
 /* src[i]: bf16 NHWC sources; wpacked: bf16 [Cout_pad][Ktot]; bias: f32 [Cout_pad] (nullable);
- * out: bf16 or f32 view; stats_sum / stats_sq: f32 [Cout_pad] accumulators (nullable) that receive
+ * out: bf16 or f32 view; stats_sum / stats_sq: f32 [stat_groups][Cout_pad] accumulators (nullable) that receive
  * per-channel sum and sum of squares of the PRE-bias accumulators (for batch-norm statistics,
  * models/networks/layers.py:13-14) via atomic adds.                                                */
 int kp_tapconv_bf16(const kp_tapconv_desc* desc, const void* const* src, const void* wpacked, const float* bias,
@@ -224,14 +229,20 @@ int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int r
 int kp_bn_stats_apply(const float* stats_sum, const float* stats_sq, const float* conv_bias, const float* gamma,
                       const float* beta, double count, float eps, float decay, float* moving_mean, float* moving_var,
                       float* scale, float* shift, float* save_mean, float* save_rstd, const void* x, int relu, int upsample,
-                      int N, int H, int W, int C, void* out, void* stream);
+                      int N, int H, int W, int C, void* out, int segments, void* stream);
+/* segments > 1: the batch is `segments` equal runs of images that are normalised with their OWN statistics (two calls of
+ * a shared-weight network executed as one launch, see kp_tapconv_desc.stat_groups): stats_sum / stats_sq / scale / shift /
+ * save_mean / save_rstd are [segments][C], count is the pixel count of ONE segment, and the moving averages receive one
+ * update per segment, in order.                                                                           */
 /* backward of kp_bn_act_apply + batch-norm statistics: dout (grad of the output, upsampled size if upsample),
  * x (the conv output saved by the forward) -> dbeta, dgamma f32 [C] (this call's sums; zeroed by the library
  * unless prezeroed != 0) and dx bf16 [N,H,W,C].  gbeta_acc / ggamma_acc (nullable): parameter-gradient buffers
  * that additionally receive += dbeta / dgamma.                                                          */
 int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
                   const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, void* stream);
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, int segments, void* stream);
+/* (segments as in kp_bn_stats_apply: scale / shift / save_mean / save_rstd / dbeta / dgamma are [segments][C]; gbeta_acc /
+ * ggamma_acc receive the sum over the segments.)                                                              */
 /* adjoint of tf.image.resize_images x2 (legacy bilinear, models/networks/__init__.py:63,98) alone:
  * dout bf16 [N,2H,2W,C] -> dact bf16 [N,H,W,C].  The BN backward of the upsampling layers runs this once and then the
  * plain (upsample = 0) kp_bn_act_bwd on dact.                                                                 */

@@ -58,8 +58,12 @@ def test_argument_validation_of_conv_and_bn_entry_points(lib_built):
     from kp_b200 import tapconv as tc
     # kp_bn_stats_apply: NULL statistics
     rc = h.kp_bn_stats_apply(None, None, None, None, None, 16.0, 1e-5, 0.999, None, None, None, None, None, None, None, 1, 0,
-                             1, 4, 4, 16, None, None)
+                             1, 4, 4, 16, None, 1, None)
     assert rc == -1 and b"kp_bn_stats_apply" in h.kp_last_error()
+    # ... and a batch that does not split into the requested number of statistics segments
+    rc = h.kp_bn_stats_apply(None, None, None, None, None, 16.0, 1e-5, 0.999, None, None, None, None, None, None, None, 1, 0,
+                             3, 4, 4, 16, None, 2, None)
+    assert rc == -1 and b"segments" in h.kp_last_error()
     # kp_upsample2x_bwd: bad shape, then NULL tensors
     assert h.kp_upsample2x_bwd(None, 0, 4, 4, 16, None, None) == -1
     assert h.kp_upsample2x_bwd(None, 1, 4, 4, 16, None, None) == -1

@@ -96,26 +96,37 @@ def _cuda_grads(model, im, fut, which, trace=None):
 
 
 def _substitutions(trace, which, B):
-    """engine trace -> oracle substitution lists.  The two implementations batch differently: the CUDA path runs VGG on
-    gt and on pred separately (oracle: one call on [gt; pred]) and, in the D run, img_discr once on [real; fake]
+    """engine trace -> oracle substitution lists.  The two implementations batch differently: the CUDA path runs the two
+    pose_encoder calls as ONE pass over [image; future_image] with per-segment statistics (oracle: two calls), VGG once on
+    [gt; pred] like the oracle (or separately with KP_BATCH_SHARED=0), and, in the D run, img_discr once on [real; fake]
     (oracle: two calls)."""
     sub = {}
 
     def add(name, t):
         sub.setdefault(name, []).append(t.detach().double().cpu())
+
+    def add_calls(name, t, calls, per_call_vector=False):
+        """a tensor that holds `calls` calls side by side (batch segments, or [segments*C] vectors)"""
+        n = t.shape[0] // calls
+        for c in range(calls):
+            add(name, t[c * n:(c + 1) * n])
     for e in trace:
         sc = e["scope"]
         if e["kind"] == "bn":
-            add(sc + ":pre", e["y_pre"]); add(sc + ":mean", e["mean"]); add(sc + ":rstd", e["rstd"]); add(sc, e["out"])
+            sg = e.get("segments", 1)
+            add_calls(sc + ":pre", e["y_pre"], sg); add_calls(sc + ":mean", e["mean"], sg); add_calls(sc + ":rstd", e["rstd"], sg)
+            add_calls(sc, e["out"], sg)
         elif e["kind"] == "k1":
-            add("mu", e["mu"]); add("maps", e["maps"])
+            calls = e["mu"].shape[0] // B
+            add_calls("mu", e["mu"], calls); add_calls("maps", e["maps"], calls)
         elif sc == "translator/conv_6_0":
             add(sc, e["out"][..., :3]); add("translator/conv_6_1:sigmoid", e["out"][..., 3:4])
+        elif sc.startswith("pose_encoder/"):
+            add_calls(sc, e["out"], e["out"].shape[0] // B)          # the 1x1 head: logits of one or two calls
         else:
             add(sc, e["out"])
     for name in list(sub):
-        if name.startswith("vgg/"):
-            assert len(sub[name]) == 2
+        if name.startswith("vgg/") and len(sub[name]) == 2:           # separate gt / pred passes
             sub[name] = [torch.cat(sub[name], dim=0)]
         if name.startswith("img_discr/") and which == "D":
             assert len(sub[name]) == 1 and sub[name][0].shape[0] == 2 * B

@@ -39,11 +39,11 @@ SIGNATURES = {
     "kp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_double, c_float, c_float, c_vp, c_vp, c_vp, c_vp,
                        c_vp, c_vp, c_vp],
     "kp_bn_stats_apply": [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_float, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                          c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+                          c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp],
     "kp_upsample2x_bwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_apply": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_bn_act_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
-                      c_vp, c_vp, c_int, c_vp],
+                      c_vp, c_vp, c_int, c_int, c_vp],
     "kp_act_mask_bwd": [c_vp, c_vp, c_float, c_ll, c_vp, c_vp],
     "kp_maxpool2x2_fwd": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "kp_maxpool2x2_bwd": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],

@@ -134,7 +134,7 @@ def pad_vec(v, n):
 
 
 def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None, cout_written=None, tile=None, bn=0,
-             accumulate=False):
+             accumulate=False, stat_groups=1):
     """Launch one tap-GEMM.  srcs: bf16 NHWC CUDA tensors; out: bf16 or f32 tensor written through the plan's
     output view; bias: f32 [rows_pad] or None; stats: (sum, sumsq) f32 [rows_pad] accumulators or None."""
     for s in srcs:
@@ -148,15 +148,17 @@ def run_plan(plan, srcs, wpacked, bias, out, act=ACT_NONE, alpha=0.0, stats=None
     if bias is not None and (bias.dtype != torch.float32 or bias.shape[0] != plan.rows_pad):
         raise ValueError("bias must be f32 [rows_pad]")
     d = plan.desc(act=act, alpha=alpha, out_f32=(out.dtype == torch.float32), cout_written=cout_written, tile=tile, bn=bn,
-                  accumulate=accumulate)
+                  accumulate=accumulate, stat_groups=stat_groups)
     ptrs = (ctypes.c_void_p * tc.KP_MAX_MAPS)()
     for i, s in enumerate(srcs):
         ptrs[i] = s.data_ptr()
     ssum = ssq = None
     if stats is not None:
         ssum, ssq = stats
-        if ssum.dtype != torch.float32 or ssum.shape[0] != plan.rows_pad or ssq.shape[0] != plan.rows_pad:
-            raise ValueError("stats buffers must be f32 [rows_pad]")
+        if ssum.dtype != torch.float32 or ssum.numel() != stat_groups * plan.rows_pad or ssq.numel() != stat_groups * plan.rows_pad:
+            raise ValueError("stats buffers must be f32 [stat_groups * rows_pad]")
+        if plan.N % stat_groups != 0:
+            raise ValueError("batch %d does not split into %d statistics segments" % (plan.N, stat_groups))
     first = plan.taps[0][2]
     k_real = len(plan.taps) * sum(plan.views[first + s]["C"] for s in range(plan.n_src))
     flops = 2.0 * plan.N * plan.Ho * plan.Wo * k_real * plan.rows * getattr(plan, "flop_scale", 1.0)

@@ -54,6 +54,7 @@ struct alignas(64) Halo2KParams {
     int TB, resident;
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int Ho, Wo, N, BN, tmem_cols;
+    int sgroups, group_n;                            // batch-norm statistics per batch segment of group_n images
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
     int Cout, cout_pad, out_f32, act, accumulate, ksplit;
@@ -271,9 +272,10 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
         const int et = threadIdx.x - 128;
         for (int i = et; i < p.cout_pad; i += 128) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
         if (p.ssum != nullptr)
-            for (int i = et; i < 8 * p.cout_pad; i += 128) s_stat[i] = 0.f;     // four warp-private copies of [2][cout_pad]
+            for (int i = et; i < 8 * p.sgroups * p.cout_pad; i += 128) s_stat[i] = 0.f;     // four warp-private copies of [G][2][cout_pad]
         named_bar_sync(1, 128);
-        float* const s_stat_w = s_stat + (warp - 4) * 2 * p.cout_pad;
+        float* const s_stat_w0 = s_stat + (warp - 4) * p.sgroups * 2 * p.cout_pad;
+        const int group_n = p.group_n, gstride = 2 * p.cout_pad;
         if (EPI != 0) {
             // fast epilogue: everything that is constant for the launch sits in registers, the chunk is branch-free
             const EpiFast ef = {p.slope, p.cout_pad};
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
                 const int n_off = nt * BN;
                 const int acc = acc_bufs == 2 ? (lt & 1) : 0;
                 const int uw = w0 + tw;
+                float* const s_stat_w = s_stat_w0 + (n / group_n) * gstride;       // this image's statistics segment
                 __nv_bfloat16* const o_n = outp + (long long)n * out_sn + (long long)uw * out_sw + n_off;
                 if (et == 0) KP_H2TRACE(5, lt);
                 mbar_wait(&tfull[acc], (lt / acc_bufs) & 1);
@@ -338,6 +341,7 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
                 const int tr = h2_fdiv(r, p.rcp_tw);
                 const int h0 = tr * TILE_ROWS, w0 = (r - tr * p.tiles_w) * 8;
                 const int n_off = nt * p.BN;
+                float* const s_stat_w = s_stat_w0 + (n / group_n) * gstride;
                 const int acc = p.acc_bufs == 2 ? (lt & 1) : 0;
                 if (et == 0) KP_H2TRACE(5, lt);
                 mbar_wait(&tfull[acc], (lt / p.acc_bufs) & 1);
@@ -371,10 +375,12 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
-            const int cp = p.cout_pad;
-            for (int i = et; i < cp; i += 128) {
-                atomicAdd(p.ssum + i, s_stat[i] + s_stat[2 * cp + i] + s_stat[4 * cp + i] + s_stat[6 * cp + i]);
-                atomicAdd(p.ssq + i, s_stat[cp + i] + s_stat[3 * cp + i] + s_stat[5 * cp + i] + s_stat[7 * cp + i]);
+            const int cp = p.cout_pad, G = p.sgroups, ws = G * 2 * cp;      // ws: stride between the warps' copies
+            for (int i = et; i < G * cp; i += 128) {
+                const int g = i / cp, c = i - g * cp;
+                const float* b = s_stat + g * 2 * cp + c;
+                atomicAdd(p.ssum + i, b[0] + b[ws] + b[2 * ws] + b[3 * ws]);
+                atomicAdd(p.ssq + i, b[cp] + b[ws + cp] + b[2 * ws + cp] + b[3 * ws + cp]);
             }
         }
     }
@@ -523,7 +529,11 @@ int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* w
     p.a_slot_bytes = ((uint32_t)(p.R * p.pitch) * (uint32_t)max_nch * 2u + 1023u) & ~1023u;
     p.b_bytes = (uint32_t)BN * 128u;
     auto rcp32 = [](int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); };
-    const uint32_t epi_bytes = (ssum != nullptr ? 9u : 1u) * (uint32_t)d->Cout_pad * sizeof(float);   // bias (+ four warp-private [2][Cout_pad] statistics)
+    const int G = d->stat_groups > 1 ? d->stat_groups : 1;
+    KP_REQUIRE(d->N % G == 0, "kp_tapconv(halo2): %d images do not split into %d statistics segments", d->N, G);
+    p.sgroups = G; p.group_n = d->N / G;
+    // bias (+ four warp-private [G][2][Cout_pad] statistics)
+    const uint32_t epi_bytes = (ssum != nullptr ? 1u + 8u * (uint32_t)G : 1u) * (uint32_t)d->Cout_pad * sizeof(float);
     const uint32_t all_b = (uint32_t)(ns * d->n_taps) * p.b_bytes;
     const uint32_t fixed = epi_bytes + 1024u + 512u;
     // Two CTAs per SM whenever one CTA fits half of the SM's shared memory and TMEM: two independent TMA / issue /

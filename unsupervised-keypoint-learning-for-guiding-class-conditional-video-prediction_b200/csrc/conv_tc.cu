@@ -40,6 +40,7 @@ struct alignas(64) TapConvKParams {
     void* out;
     long long out_off, out_sw, out_sh, out_sn;
     int Cout, cout_pad, out_f32, act, accumulate;
+    int sgroups, group_n;      // batch-norm statistics per batch segment of group_n images (tiles never straddle segments)
     float alpha, slope;
     const float* bias;
     float* ssum;
@@ -218,9 +219,10 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         const int et = threadIdx.x - 64;
         for (int i = et; i < p.cout_pad; i += 128) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.f;
         if (p.ssum != nullptr)
-            for (int i = et; i < 8 * p.cout_pad; i += 128) s_stat[i] = 0.f;      // four warp-private copies of [2][cout_pad]
+            for (int i = et; i < 8 * p.sgroups * p.cout_pad; i += 128) s_stat[i] = 0.f;      // four warp-private copies of [G][2][cout_pad]
         named_bar_sync(1, 128);
-        float* const s_stat_w = s_stat + (warp - 2) * 2 * p.cout_pad;
+        float* const s_stat_w0 = s_stat + (warp - 2) * p.sgroups * 2 * p.cout_pad;
+        const int group_n = p.group_n, gstride = 2 * p.cout_pad;
         int lt = 0;
         if (EPI != 0) {
             // fast epilogue (ksplit == 1): launch constants in registers, branch-free chunks
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
                 const int n_off = nt * BN;
                 const int uw = w0 + tw, uh = h0 + th, n = n0 + tn;
                 const bool valid = (uw < Wo) && (uh < Ho) && (n < N);
+                float* const s_stat_w = s_stat_w0 + (n0 / group_n) * gstride;     // the tile's statistics segment (warp-uniform)
                 __nv_bfloat16* const o_p = outp + (long long)n * out_sn + (long long)uh * out_sh + (long long)uw * out_sw + n_off;
                 const int acc = lt & 1;
                 mbar_wait(&tfull[acc], (lt >> 1) & 1);
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
             const int n_off = nt * p.BN;
             const int uw = w0 + tw, uh = h0 + th, n = n0 + tn;
             const bool valid = (uw < p.Wo) && (uh < p.Ho) && (n < p.N);
+            float* const s_stat_w = s_stat_w0 + (n0 / group_n) * gstride;
             const long long pix = p.out_off + (long long)n * p.out_sn + (long long)uh * p.out_sh + (long long)uw * p.out_sw;
             const int acc = lt & 1;
             if (threadIdx.x == 64) KP_TTRACE(4, lt);
@@ -299,10 +303,12 @@ __global__ void __launch_bounds__(192, 1) tapconv_kernel(const __grid_constant__
         }
         if (p.ssum != nullptr) {
             named_bar_sync(1, 128);
-            const int cp = p.cout_pad;
-            for (int i = et; i < cp; i += 128) {
-                atomicAdd(p.ssum + i, s_stat[i] + s_stat[2 * cp + i] + s_stat[4 * cp + i] + s_stat[6 * cp + i]);
-                atomicAdd(p.ssq + i, s_stat[cp + i] + s_stat[3 * cp + i] + s_stat[5 * cp + i] + s_stat[7 * cp + i]);
+            const int cp = p.cout_pad, G = p.sgroups, ws = G * 2 * cp;      // ws: stride between the warps' copies
+            for (int i = et; i < G * cp; i += 128) {
+                const int g = i / cp, c = i - g * cp;
+                const float* b = s_stat + g * 2 * cp + c;
+                atomicAdd(p.ssum + i, b[0] + b[ws] + b[2 * ws] + b[3 * ws]);
+                atomicAdd(p.ssq + i, b[cp] + b[ws + cp] + b[2 * ws + cp] + b[3 * ws + cp]);
             }
         }
     }
@@ -418,15 +424,18 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     // stride-1 multi-tap layers: halo-tile kernels (each input element is fetched once per tile instead of once per tap);
     // the TMA-staged one first, the cp.async gather kernel for what it does not take (8-channel slots)
     if (halo2_eligible(d, ssum)) return halo2_launch(d, src, wpacked, bias, out, ssum, ssq, st);
-    if (haloconv_eligible(d, ssum)) return haloconv_launch(d, src, wpacked, bias, out, ssum, ssq, st);
+    const bool segmented = d->stat_groups > 1 && ssum != nullptr;      // only the two kernels below keep per-segment statistics
+    if (!segmented && haloconv_eligible(d, ssum)) return haloconv_launch(d, src, wpacked, bias, out, ssum, ssq, st);
     // wide layers, experimental: CTA pairs (cta_group::2) halve the weight fill per SM
-    if (tapconv2_eligible(d)) return tapconv2_launch(d, src, wpacked, bias, out, ssum, ssq, st);
+    if (!segmented && tapconv2_eligible(d)) return tapconv2_launch(d, src, wpacked, bias, out, ssum, ssq, st);
 
     TapConvKParams p;
     memset(&p, 0, sizeof(p));
     const int CB = d->CB;
     int TW = d->TW, TH = d->TH, TN = d->TN, BN = d->BN;
-    if (TW <= 0 || TH <= 0 || TN <= 0) choose_pixel_tile(128, d->Wo, d->Ho, d->N, &TW, &TH, &TN);
+    // with per-segment statistics a tile must not straddle two segments: choose the image count per tile for one segment
+    if (TW <= 0 || TH <= 0 || TN <= 0)
+        choose_pixel_tile(128, d->Wo, d->Ho, (d->stat_groups > 1 && ssum != nullptr) ? d->N / d->stat_groups : d->N, &TW, &TH, &TN);
     KP_REQUIRE(TW * TH * TN == 128, "kp_tapconv: tile %dx%dx%d is not 128 pixels", TW, TH, TN);
     if (BN <= 0) {
         BN = d->Cout_pad <= 256 ? d->Cout_pad : (d->Cout_pad % 256 == 0 ? 256 : 128);
@@ -525,7 +534,12 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     // issuers; the 256-wide tiles need all 512 TMEM columns and most of the shared memory, so they run alone.
     // Short-K tiles (<= 8 K groups, narrow channel tile) are bound by the latency of the epilogue chain, not by the
     // tensor pipe: a third CTA per SM adds epilogue warps.
-    const uint32_t epi_bytes = (ssum != nullptr ? 9u : 1u) * (uint32_t)d->Cout_pad * sizeof(float);   // bias (+ four warp-private [2][Cout_pad] statistics)
+    const int SG = d->stat_groups > 1 ? d->stat_groups : 1;
+    KP_REQUIRE(d->N % SG == 0 && (SG == 1 || (d->N / SG) % TN == 0),
+               "kp_tapconv: %d images do not split into %d statistics segments of whole %d-image tiles", d->N, SG, TN);
+    p.sgroups = SG; p.group_n = d->N / SG;
+    // bias (+ four warp-private [G][2][Cout_pad] statistics)
+    const uint32_t epi_bytes = (ssum != nullptr ? 1u + 8u * (uint32_t)SG : 1u) * (uint32_t)d->Cout_pad * sizeof(float);
     int ctas_per_sm = p.tmem_cols <= 256 ? 2 : 1;
     if (p.tmem_cols <= 128 && p.groups_per_split <= 8) ctas_per_sm = 3;
     if (p.tmem_cols <= 128 && p.groups_per_split <= 1) ctas_per_sm = 4;   // one K group per tile: pure epilogue/latency work

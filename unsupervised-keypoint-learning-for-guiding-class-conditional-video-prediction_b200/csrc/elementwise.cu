@@ -125,10 +125,15 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
     extern __shared__ float sp[];   // [2][C]
     pdl_launch_dependents();
     pdl_wait();
+    // Batch segments (gridDim.y of them, N images each) are normalised with their OWN statistics: the two calls of the
+    // shared pose_encoder run as one launch on [image; future_image].  All per-segment vectors are [segments][C].
+    const int seg = blockIdx.y;
+    x += (long long)seg * N * H * W * C;
+    out += (long long)seg * N * H * W * C * (UPSAMPLE ? 4 : 1);
     if (fin.ssum != nullptr) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const double m0 = (double)fin.ssum[c] / fin.count;
-            double var = (double)fin.ssq[c] / fin.count - m0 * m0;
+            const double m0 = (double)fin.ssum[seg * C + c] / fin.count;
+            double var = (double)fin.ssq[seg * C + c] / fin.count - m0 * m0;
             if (var < 0.0) var = 0.0;
             const float mean = (float)m0 + (fin.bias ? fin.bias[c] : 0.f);
             const float rstd = rsqrtf((float)var + fin.eps);
@@ -137,21 +142,32 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
             sp[c] = sc;
             sp[C + c] = sh;
             if (blockIdx.x == 0) {
-                fin.scale[c] = sc;
-                fin.shift[c] = sh;
-                if (fin.save_mean) fin.save_mean[c] = mean;
-                if (fin.save_rstd) fin.save_rstd[c] = rstd;
-                if (fin.moving_mean) {
-                    const float unbiased = (float)(var * (fin.count / fmax(fin.count - 1.0, 1.0)));
-                    fin.moving_mean[c] = fin.moving_mean[c] * fin.decay + mean * (1.f - fin.decay);
-                    fin.moving_var[c] = fin.moving_var[c] * fin.decay + unbiased * (1.f - fin.decay);
+                fin.scale[seg * C + c] = sc;
+                fin.shift[seg * C + c] = sh;
+                if (fin.save_mean) fin.save_mean[seg * C + c] = mean;
+                if (fin.save_rstd) fin.save_rstd[seg * C + c] = rstd;
+                if (fin.moving_mean && seg == 0) {
+                    // one thread per channel applies the moving-average updates of ALL segments, in call order (the
+                    // reference runs one update op per pose_encoder call)
+                    float mm = fin.moving_mean[c], mv = fin.moving_var[c];
+                    for (int g = 0; g < (int)gridDim.y; ++g) {
+                        const double gm0 = (double)fin.ssum[g * C + c] / fin.count;
+                        double gvar = (double)fin.ssq[g * C + c] / fin.count - gm0 * gm0;
+                        if (gvar < 0.0) gvar = 0.0;
+                        const float gmean = (float)gm0 + (fin.bias ? fin.bias[c] : 0.f);
+                        const float unbiased = (float)(gvar * (fin.count / fmax(fin.count - 1.0, 1.0)));
+                        mm = mm * fin.decay + gmean * (1.f - fin.decay);
+                        mv = mv * fin.decay + unbiased * (1.f - fin.decay);
+                    }
+                    fin.moving_mean[c] = mm;
+                    fin.moving_var[c] = mv;
                 }
             }
         }
     } else {
         for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            sp[i] = scale ? scale[i] : 1.f;
-            sp[C + i] = scale ? shift[i] : 0.f;
+            sp[i] = scale ? scale[seg * C + i] : 1.f;
+            sp[C + i] = scale ? shift[seg * C + i] : 0.f;
         }
     }
     __syncthreads();
@@ -284,6 +300,12 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
                          float* __restrict__ dgamma) {
     pdl_launch_dependents();
     pdl_wait();
+    {   // batch segment blockIdx.y (N images each): own statistics, own sums; all per-segment vectors are [segments][C]
+        const int seg = blockIdx.y;
+        dout += (long long)seg * N * H * W * C * (UPSAMPLE ? 4 : 1);
+        x += (long long)seg * N * H * W * C;
+        scale += seg * C; shift += seg * C; mean += seg * C; rstd += seg * C; dbeta += seg * C; dgamma += seg * C;
+    }
     const int CG = C >> 3;                 // power of two, <= 256
     const int cg = threadIdx.x % CG;
     const int lanes = blockDim.x / CG;     // pixel lanes per block
@@ -370,11 +392,19 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloa
     extern __shared__ float sp[];   // [4][C]: sc, sh, k1, k0
     pdl_launch_dependents();
     pdl_wait();
+    {
+        const int seg = blockIdx.y;
+        dout += (long long)seg * N * H * W * C * (UPSAMPLE ? 4 : 1);
+        x += (long long)seg * N * H * W * C;
+        dx += (long long)seg * N * H * W * C;
+        scale += seg * C; shift += seg * C; mean += seg * C; rstd += seg * C; dbeta += seg * C; dgamma += seg * C;
+    }
     if (blockIdx.x == 0 && gbeta_acc != nullptr) {
-        // fold this call's dbeta / dgamma into the parameter-gradient buffers (the shared pose_encoder accumulates two calls)
+        // fold this segment's dbeta / dgamma into the parameter-gradient buffers (the shared pose_encoder accumulates its two
+        // calls; with several segments in one launch the blocks (0, seg) add concurrently, hence atomics)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            gbeta_acc[c] += dbeta[c];
-            ggamma_acc[c] += dgamma[c];
+            atomicAdd(gbeta_acc + c, dbeta[c]);
+            atomicAdd(ggamma_acc + c, dgamma[c]);
         }
     }
     const float inv_n = 1.0f / (float)((long long)N * H * W);
@@ -792,15 +822,17 @@ int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const
     return KP_OK;
 }
 static int bn_apply_launch(const void* x, const float* scale, const float* shift, const BnFin& fin, int relu, int upsample, int N,
-                           int H, int W, int C, void* out, cudaStream_t st) {
+                           int H, int W, int C, void* out, cudaStream_t st, int groups = 1) {
     KP_REQUIRE(C % 8 == 0, "bn_act_apply: C=%d must be a multiple of 8", C);
     KP_REQUIRE(C <= 4096, "bn_act_apply: C=%d too large", C);
+    KP_REQUIRE(groups >= 1 && N % groups == 0, "bn_act_apply: %d images do not split into %d segments", N, groups);
+    N /= groups;                                                 // images per segment; segments on grid.y
     const long long total = (long long)N * H * W * (C / 8);     // input vectors (one thread-item each)
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     const size_t smem = 2 * (size_t)C * sizeof(float);
-    if (upsample) KP_CUDA_CHECK(launch_pdl(bn_act_apply_kernel<true>, dim3(grid_for(total, 256)), dim3(256), smem, st, xi, scale, shift, fin, relu, N, H, W, C, o));
-    else KP_CUDA_CHECK(launch_pdl(bn_act_apply_kernel<false>, dim3(grid_for((total + 1) / 2, 256)), dim3(256), smem, st, xi, scale, shift, fin, relu, N, H, W, C, o));
+    if (upsample) KP_CUDA_CHECK(launch_pdl(bn_act_apply_kernel<true>, dim3(grid_for(total, 256, 148 * 16 / groups), groups), dim3(256), smem, st, xi, scale, shift, fin, relu, N, H, W, C, o));
+    else KP_CUDA_CHECK(launch_pdl(bn_act_apply_kernel<false>, dim3(grid_for((total + 1) / 2, 256, 148 * 16 / groups), groups), dim3(256), smem, st, xi, scale, shift, fin, relu, N, H, W, C, o));
     KP_LAUNCHED();
     return KP_OK;
 }
@@ -812,34 +844,36 @@ int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int r
 }
 int ew_bn_stats_apply(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, double count,
                       float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean, float* srstd,
-                      const void* x, int relu, int upsample, int N, int H, int W, int C, void* out, cudaStream_t st) {
+                      const void* x, int relu, int upsample, int N, int H, int W, int C, void* out, int groups, cudaStream_t st) {
     BnFin fin = {ssum, ssq, bias, gamma, beta, (float)count, eps, decay, mm, mv, scale, shift, smean, srstd};
-    return bn_apply_launch(x, nullptr, nullptr, fin, relu, upsample, N, H, W, C, out, st);
+    return bn_apply_launch(x, nullptr, nullptr, fin, relu, upsample, N, H, W, C, out, st, groups);
 }
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
                   const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, cudaStream_t st) {
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, int groups, cudaStream_t st) {
     KP_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_act_bwd: C=%d must be 8 x a power of two <= 2048", C);
+    KP_REQUIRE(groups >= 1 && N % groups == 0, "bn_act_bwd: %d images do not split into %d segments", N, groups);
+    N /= groups;                                                 // images per segment; segments on grid.y
     const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dout);
     const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
     if (!prezeroed) {
-        KP_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
-        KP_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
+        KP_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, (size_t)groups * C * sizeof(float), st));
+        KP_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, (size_t)groups * C * sizeof(float), st));
     }
     const long long P = (long long)N * H * W;
     const int lanes = 256 / (C / 8);
-    const int rgrid = grid_for((P + 2 * lanes - 1) / (2 * lanes), 1, 148 * 6);
+    const int rgrid = grid_for((P + 2 * lanes - 1) / (2 * lanes), 1, 148 * 6 / groups);
     if (upsample)
-        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_reduce_kernel<true>, dim3(rgrid), dim3(256), 0, st, d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma));
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_reduce_kernel<true>, dim3(rgrid, groups), dim3(256), 0, st, d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma));
     else
-        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_reduce_kernel<false>, dim3(rgrid), dim3(256), 0, st, d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma));
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_reduce_kernel<false>, dim3(rgrid, groups), dim3(256), 0, st, d, xi, scale, shift, mean, rstd, relu, N, H, W, C, dbeta, dgamma));
     KP_LAUNCHED();
     const long long total = P * (C / 8);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dx);
     if (upsample)
-        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_apply_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 4 * (size_t)C * sizeof(float), st, d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc));
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_apply_kernel<true>, dim3(grid_for(total, 256, 148 * 16 / groups), groups), dim3(256), 4 * (size_t)C * sizeof(float), st, d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc));
     else
-        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_apply_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 4 * (size_t)C * sizeof(float), st, d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc));
+        KP_CUDA_CHECK(launch_pdl(bn_act_bwd_apply_kernel<false>, dim3(grid_for(total, 256, 148 * 16 / groups), groups), dim3(256), 4 * (size_t)C * sizeof(float), st, d, xi, scale, shift, mean, rstd, dbeta, dgamma, relu, N, H, W, C, o, gbeta_acc, ggamma_acc));
     KP_LAUNCHED();
     return KP_OK;
 }

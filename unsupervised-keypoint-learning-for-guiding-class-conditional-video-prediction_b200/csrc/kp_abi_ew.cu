@@ -44,23 +44,25 @@ int kp_bn_act_apply(const void* x, const float* scale, const float* shift, int r
 int kp_bn_stats_apply(const float* stats_sum, const float* stats_sq, const float* conv_bias, const float* gamma,
                       const float* beta, double count, float eps, float decay, float* moving_mean, float* moving_var,
                       float* scale, float* shift, float* save_mean, float* save_rstd, const void* x, int relu, int upsample,
-                      int N, int H, int W, int C, void* out, void* stream) {
+                      int N, int H, int W, int C, void* out, int segments, void* stream) {
     KP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && count > 0, "%s: bad shape", __func__);
+    KP_REQUIRE(segments >= 1 && N % segments == 0, "%s: %d images do not split into %d segments", __func__, N, segments);
     KP_NONNULL(stats_sum); KP_NONNULL(stats_sq); KP_NONNULL(gamma); KP_NONNULL(beta); KP_NONNULL(scale); KP_NONNULL(shift);
     KP_NONNULL(x); KP_NONNULL(out);
     KP_REQUIRE((moving_mean == nullptr) == (moving_var == nullptr), "%s: moving_mean and moving_var go together", __func__);
     return ew_bn_stats_apply(stats_sum, stats_sq, conv_bias, gamma, beta, count, eps, decay, moving_mean, moving_var, scale,
-                             shift, save_mean, save_rstd, x, relu, upsample, N, H, W, C, out, ST);
+                             shift, save_mean, save_rstd, x, relu, upsample, N, H, W, C, out, segments, ST);
 }
 int kp_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* save_mean,
                   const float* save_rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, void* stream) {
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, int segments, void* stream) {
     KP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", __func__);
+    KP_REQUIRE(segments >= 1 && N % segments == 0, "%s: %d images do not split into %d segments", __func__, N, segments);
     KP_NONNULL(dout); KP_NONNULL(x); KP_NONNULL(scale); KP_NONNULL(shift); KP_NONNULL(save_mean); KP_NONNULL(save_rstd);
     KP_NONNULL(dbeta); KP_NONNULL(dgamma); KP_NONNULL(dx);
     KP_REQUIRE((gbeta_acc == nullptr) == (ggamma_acc == nullptr), "%s: gbeta_acc and ggamma_acc go together", __func__);
     return ew_bn_act_bwd(dout, x, scale, shift, save_mean, save_rstd, relu, upsample, N, H, W, C, dbeta, dgamma, dx, gbeta_acc,
-                         ggamma_acc, prezeroed, ST);
+                         ggamma_acc, prezeroed, segments, ST);
 }
 int kp_upsample2x_bwd(const void* dout, int N, int H, int W, int C, void* dact, void* stream) {
     KP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "%s: bad shape", __func__);

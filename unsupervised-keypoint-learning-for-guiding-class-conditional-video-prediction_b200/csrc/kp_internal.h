@@ -61,12 +61,12 @@ int ew_bn_finalize(const float* ssum, const float* ssq, const float* bias, const
                    float* srstd, cudaStream_t st);
 int ew_bn_stats_apply(const float* ssum, const float* ssq, const float* bias, const float* gamma, const float* beta, double count,
                       float eps, float decay, float* mm, float* mv, float* scale, float* shift, float* smean, float* srstd,
-                      const void* x, int relu, int upsample, int N, int H, int W, int C, void* out, cudaStream_t st);
+                      const void* x, int relu, int upsample, int N, int H, int W, int C, void* out, int groups, cudaStream_t st);
 int ew_bn_act_apply(const void* x, const float* scale, const float* shift, int relu, int upsample, int N, int H, int W, int C,
                     void* out, cudaStream_t st);
 int ew_bn_act_bwd(const void* dout, const void* x, const float* scale, const float* shift, const float* mean,
                   const float* rstd, int relu, int upsample, int N, int H, int W, int C, float* dbeta, float* dgamma,
-                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, cudaStream_t st);
+                  void* dx, float* gbeta_acc, float* ggamma_acc, int prezeroed, int groups, cudaStream_t st);
 int ew_upsample2x_bwd(const void* dout, int N, int H, int W, int C, void* dact, cudaStream_t st);
 int ew_act_mask_bwd(const void* dy, const void* y, float alpha, long long n_elems, void* g, cudaStream_t st);
 int ew_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, cudaStream_t st);

@@ -260,13 +260,18 @@ def _bias_vec(ctx, bnames, rows_pad):
 
 
 def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode=False, act=tc.ACT_NONE, alpha=0.0,
-               upsample=False, out_f32=False, need_input_grad=True, wshape=None):
+               upsample=False, out_f32=False, need_input_grad=True, wshape=None, segments=1, grad_rows=None):
     """layers.conv [+ layers.batch_norm + relu] [+ resize x2] of the reference, on bf16 NHWC tensors.
 
     srcs: list of bf16 [N,H,W,C] tensors (virtual channel concat).  Returns the layer output (bf16, or f32 when
     out_f32).  bn: BN scope name or None.  With bn and train_mode the batch statistics are used (and the
     moving averages updated when ctx.update_moving); with bn and not train_mode BN is folded into the
     convolution.  A tape entry is recorded when ctx.tape is set.
+    segments > 1: the batch holds that many calls of a shared-weight network side by side (pose_encoder on image and
+    future_image, detector_translator_model.py:166-167): one launch per layer, batch-norm statistics, moving-average
+    updates and the BN backward per segment, exactly as separate calls would compute them.
+    grad_rows=(lo, hi): only the images [lo, hi) of the batch carry a gradient (VGG on [gt; pred], :274-279): the
+    backward pass runs on that contiguous slice alone.
     """
     wnames = [wnames] if isinstance(wnames, str) else list(wnames)
     if isinstance(bnames, str):
@@ -307,18 +312,20 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
 
     if bn is not None:
         # training-mode BN: conv (+bias) with statistics in the epilogue -> finalize -> normalise + ReLU (+ x2)
-        ssum = ctx.zeros(fplan.rows_pad)
-        ssq = ctx.zeros(fplan.rows_pad)
+        assert fplan.rows_pad == cout or segments == 1, "segmented batch norm needs Cout to be a multiple of 16"
+        ssum = ctx.zeros(segments * fplan.rows_pad)
+        ssq = ctx.zeros(segments * fplan.rows_pad)
         y_pre = torch.empty((N, Ho, Wo, cout), device=dev, dtype=BF16)
-        cv.run_plan(fplan, srcs, wp, bias, y_pre, act=tc.ACT_NONE, stats=(ssum, ssq))
+        cv.run_plan(fplan, srcs, wp, bias, y_pre, act=tc.ACT_NONE, stats=(ssum, ssq), stat_groups=segments)
         mm = ctx.p(bn + "/moving_mean") if ctx.update_moving else None
         mv = ctx.p(bn + "/moving_variance") if ctx.update_moving else None
         out, scale, shift, mean, rstd = ops.bn_stats_apply(y_pre, ssum, ssq, bias, ctx.p(bn + "/gamma"), ctx.p(bn + "/beta"),
-                                                           N * Ho * Wo, mm, mv, relu=True, upsample=upsample)
+                                                           (N // segments) * Ho * Wo, mm, mv, relu=True, upsample=upsample,
+                                                           segments=segments)
         if ctx.debug is not None:
             ctx.debug[wnames[0].replace("/conv2d/kernel", "")] = (out, y_pre, scale, shift, mean, rstd, upsample)
         if ctx.trace is not None:
-            ctx.trace.append(dict(scope=_scope_of(wnames[0]), kind="bn", out=out, y_pre=y_pre, mean=mean, rstd=rstd))
+            ctx.trace.append(dict(scope=_scope_of(wnames[0]), kind="bn", out=out, y_pre=y_pre, mean=mean, rstd=rstd, segments=segments))
         if ctx.tape is not None:
             tape = ctx.tape
 
@@ -330,7 +337,7 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
                 dy, _, _ = ops.bn_act_bwd(dout, y_pre, scale, shift, mean, rstd, relu=True, upsample=upsample,
                                           gbeta_acc=group.g(bn + "/beta") if train else None,
                                           ggamma_acc=group.g(bn + "/gamma") if train else None,
-                                          zeroed=ctx.zeros(2 * cout))
+                                          zeroed=ctx.zeros(2 * segments * cout), segments=segments)
                 _conv_backward(ctx, tape, srcs, shapes, wnames, None, w, k, stride, pad, cout, dy, group, need_input_grad,
                                cin_real, wshape)
             tape.record(bwd)
@@ -348,19 +355,28 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
             dy = tape.grad(y)          # bf16, channels padded to a multiple of 8 for f32-output layers
             if dy is None:
                 return
+            yb, sb, shp_b = y, srcs, shapes
+            if grad_rows is not None:
+                # only a contiguous run of images carries a gradient: the whole backward works on that slice
+                lo, hi = grad_rows
+                dy, yb = dy[lo:hi], y[lo:hi]
+                sb = [s_[lo:hi] for s_ in srcs]
+                shp_b = tuple((hi - lo,) + tuple(s_[1:]) for s_ in shapes)
             if act == tc.ACT_RELU:
-                dy = ops.act_mask_bwd(dy, y, 0.0)
+                dy = ops.act_mask_bwd(dy, yb, 0.0)
             elif act == tc.ACT_LEAKY:
-                dy = ops.act_mask_bwd(dy, y, alpha)
-            _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad,
-                           cin_real, wshape)
+                dy = ops.act_mask_bwd(dy, yb, alpha)
+            _conv_backward(ctx, tape, sb, shp_b, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad,
+                           cin_real, wshape, parents=srcs if grad_rows is not None else None, rows=grad_rows)
         tape.record(bwd)
     return y
 
 
 def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad,
-                           cin_real, wshape):
-    """dy: bf16 gradient w.r.t. the convolution output, [N,Ho,Wo,cpad] with cpad = round_up(cout, 8)."""
+                           cin_real, wshape, parents=None, rows=None):
+    """dy: bf16 gradient w.r.t. the convolution output, [N,Ho,Wo,cpad] with cpad = round_up(cout, 8).
+    parents / rows: `srcs` are the image slices [rows[0], rows[1]) of `parents`; the data gradient goes into the same slice
+    of the parents' gradient buffers."""
     cpad = dy.shape[3]
     train = group.trainable and ((group is ctx.G and ctx.train_G) or (group is ctx.D and ctx.train_D))
     cin = sum(s[3] for s in shapes)
@@ -397,11 +413,15 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
     if not need_input_grad:
         return
     c0 = 0
-    for s, shp in zip(srcs, shapes):
+    for si, (s, shp) in enumerate(zip(srcs, shapes)):
         C = shp[3]
         plans = ctx.plan("dgrad", (shp, k, stride, pad, cpad, c0, cin),
                          lambda shp=shp, c0=c0, C=C: tc.plan_conv_dgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
-        dx, acc = tape.acquire(s)
+        if parents is None:
+            dx, acc = tape.acquire(s)
+        else:
+            full, acc = tape.acquire(parents[si])
+            dx = full[rows[0]:rows[1]]
         for i, p in enumerate(plans):
             p.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
             wp = ctx.packed_weight("dgrad", wnames, p, w)

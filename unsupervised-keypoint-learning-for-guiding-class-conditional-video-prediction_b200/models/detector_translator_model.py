@@ -54,6 +54,8 @@ class DetectorTranslatorModel(BaseModel):
         self._side = None                  # side stream for the overlapped discriminator update (data parallel only)
         self._d_pending = False
         self.overlap_d_update = os.environ.get("KP_OVERLAP_D_UPDATE", "1") != "0"
+        # the two pose_encoder calls and VGG(gt) / VGG(pred) run as single batched passes (KP_BATCH_SHARED=0: separate calls)
+        self.batch_shared_passes = os.environ.get("KP_BATCH_SHARED", "1") != "0"
         # data parallel: all-reduce the generator gradients in buckets (translator / pose_encoder / image_encoder, the
         # order in which the backward pass completes them) on the side stream, under the rest of the backward pass
         self.overlap_g_allreduce = os.environ.get("KP_OVERLAP_G_ALLREDUCE", "1") != "0"
@@ -129,8 +131,13 @@ class DetectorTranslatorModel(BaseModel):
         embeddings = networks.image_encoder(im, tm) if for_G_run else \
             [im] + networks.encoder(networks._prep7(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
         self._grad_bucket_marker("pose_encoder/")        # runs (in the backward pass) after BOTH pose_encoder calls are done
-        current_gauss_pt, current_pt_map = networks.pose_encoder_with_maps(im, self.n_points, tm, (32, 32))
-        future_gauss_pt, future_pt_map = networks.pose_encoder_with_maps(future_im, self.n_points, tm, (32, 32))
+        if self.batch_shared_passes:
+            # pose_encoder(im) and pose_encoder(future_im) as one pass over [im; future_im] with per-call BN statistics
+            (current_gauss_pt, current_pt_map), (future_gauss_pt, future_pt_map) = \
+                networks.pose_encoder_pair_with_maps(im, future_im, self.n_points, tm, (32, 32))
+        else:
+            current_gauss_pt, current_pt_map = networks.pose_encoder_with_maps(im, self.n_points, tm, (32, 32))
+            future_gauss_pt, future_pt_map = networks.pose_encoder_with_maps(future_im, self.n_points, tm, (32, 32))
         joint_embedding = networks.joint_embedding(embeddings[-2], current_pt_map, future_pt_map)
         self._grad_bucket_marker("translator/")          # ... after the translator's last weight gradient
         heads = networks.translator_heads(joint_embedding, tm)
@@ -168,17 +175,39 @@ class DetectorTranslatorModel(BaseModel):
         ctx = self.ctx
         loss = torch.zeros(2, device=self.device)             # [reconstruction, adversarial]
         tape = ctx.tape
-        ctx.tape = None
-        feat_gt = networks.vgg.features_from_prepared(networks.vgg.prepare(future_im, ops.VGG_PREP), need_input_grad=False)
-        ctx.tape = tape
-        xp = networks._prep_with_grad(ctx, future_im_pred, ops.VGG_PREP, networks.vgg.VGG_UNROLL) if backward else \
-            networks.vgg.prepare(future_im_pred, ops.VGG_PREP)
-        feat_pred = networks.vgg.features_from_prepared(xp, need_input_grad=backward)
-        for fg, fp in zip(feat_gt, feat_pred):
-            d = torch.empty_like(fp) if backward else None
-            ops.l1_pair(fg, fp, 1.0 / len(feat_pred), loss[0:1], d)
+        if self.batch_shared_passes:
+            # VGG on [gt; pred] in one pass like the reference (:274-279); only the generated half carries a gradient
+            B = future_im.shape[0]
+            u = networks.vgg.VGG_UNROLL
+            xp = torch.empty((2 * B, 128, 128, u[2]), device=self.device, dtype=torch.bfloat16)
+            networks.vgg.prepare(future_im, ops.VGG_PREP, out=xp[:B])
+            networks.vgg.prepare(future_im_pred, ops.VGG_PREP, out=xp[B:])
             if backward:
-                tape.set_grad(fp, d)
+                def prep_bwd():
+                    g = tape.grad(xp)
+                    if g is None:
+                        return
+                    dx, acc = tape.acquire(future_im_pred)
+                    ops.image_prep_unrolled_bwd(g[B:], dx, u[0], u[1], ops.VGG_PREP, accumulate=acc)
+                tape.record(prep_bwd)
+            feats = networks.vgg.features_from_prepared(xp, need_input_grad=backward, grad_rows=(B, 2 * B))
+            for f in feats:
+                d = torch.empty_like(f) if backward else None
+                ops.l1_pair(f[:B], f[B:], 1.0 / len(feats), loss[0:1], d[B:] if backward else None)
+                if backward:
+                    tape.set_grad(f, d)
+        else:
+            ctx.tape = None
+            feat_gt = networks.vgg.features_from_prepared(networks.vgg.prepare(future_im, ops.VGG_PREP), need_input_grad=False)
+            ctx.tape = tape
+            xp = networks._prep_with_grad(ctx, future_im_pred, ops.VGG_PREP, networks.vgg.VGG_UNROLL) if backward else \
+                networks.vgg.prepare(future_im_pred, ops.VGG_PREP)
+            feat_pred = networks.vgg.features_from_prepared(xp, need_input_grad=backward)
+            for fg, fp in zip(feat_gt, feat_pred):
+                d = torch.empty_like(fp) if backward else None
+                ops.l1_pair(fg, fp, 1.0 / len(feat_pred), loss[0:1], d)
+                if backward:
+                    tape.set_grad(fp, d)
         self._join_D()                      # the discriminator update of the D run must have landed
         fake_ = networks.img_discr(future_im_pred, need_input_grad=backward)
         d_adv = ops.bce_logits(fake_, 1.0, 1.0, loss[1:2], backward)

@@ -120,25 +120,27 @@ def _prep7(x):
     return ops.image_prep_unrolled(x, 7, 3, 32)
 
 
-def _cbr(ctx, srcs, conv_scope, bn_scope, train_mode, k=3, stride=1, upsample=False, need_input_grad=True):
+def _cbr(ctx, srcs, conv_scope, bn_scope, train_mode, k=3, stride=1, upsample=False, need_input_grad=True, segments=1):
     return E.conv_layer(ctx, srcs, conv_scope + "/conv2d/kernel", conv_scope + "/conv2d/bias", k, stride, 0, bn=bn_scope,
-                        train_mode=train_mode, upsample=upsample, need_input_grad=need_input_grad)
+                        train_mode=train_mode, upsample=upsample, need_input_grad=need_input_grad,
+                        segments=segments if train_mode else 1)
 
 
-def encoder(x, train_mode, filters=32, _scope="encoder/", _n_blocks=4):
+def encoder(x, train_mode, filters=32, _scope="encoder/", _n_blocks=4, _segments=1):
     """reference networks/__init__.py:7-26.  x: prepared (W-unrolled, see _prep7) bf16 image.  Returns the 4 block features.
     `_n_blocks=3` skips conv_7/conv_8, whose output the stage-1 graph never consumes: TF prunes
     them from the D run; the G run still executes them for their moving-average updates."""
     ctx = get_context()
     p = _scope
     block_features = []
+    sg = _segments if train_mode else 1
     x = E.conv_layer(ctx, [x], p + "conv_1/conv2d/kernel", p + "conv_1/conv2d/bias", (7, 1), 1, 0, bn=p + "b_norm_1",
-                     train_mode=train_mode, need_input_grad=False, wshape=(7, 1, 21, filters))
-    x = _cbr(ctx, [x], p + "conv_2", p + "b_norm_2", train_mode)
+                     train_mode=train_mode, need_input_grad=False, wshape=(7, 1, 21, filters), segments=sg)
+    x = _cbr(ctx, [x], p + "conv_2", p + "b_norm_2", train_mode, segments=sg)
     block_features.append(x)
     for i in range(_n_blocks - 1):
-        x = _cbr(ctx, [x], p + "conv_%d" % (i * 2 + 3), p + "b_norm_%d" % (i * 2 + 3), train_mode, stride=2)
-        x = _cbr(ctx, [x], p + "conv_%d" % (i * 2 + 4), p + "b_norm_%d" % (i * 2 + 4), train_mode)
+        x = _cbr(ctx, [x], p + "conv_%d" % (i * 2 + 3), p + "b_norm_%d" % (i * 2 + 3), train_mode, stride=2, segments=sg)
+        x = _cbr(ctx, [x], p + "conv_%d" % (i * 2 + 4), p + "b_norm_%d" % (i * 2 + 4), train_mode, segments=sg)
         block_features.append(x)
     return block_features
 
@@ -148,24 +150,26 @@ def image_encoder(x, train_mode):
     return [x] + encoder(_prep7(x), train_mode, _scope="image_encoder/encoder/")
 
 
-def pose_encoder_logits(x, n_pts, train_mode, final_res=128, filters=128):
-    """Everything of pose_encoder before get_coord (reference networks/__init__.py:36-66): fp32 logits [B,128,128,n_pts]."""
+def pose_encoder_logits(x, n_pts, train_mode, final_res=128, filters=128, _segments=1):
+    """Everything of pose_encoder before get_coord (reference networks/__init__.py:36-66): fp32 logits [B,128,128,n_pts].
+    _segments: the batch holds that many independent calls side by side (each normalised with its own batch statistics)."""
     ctx = get_context()
-    block_features = encoder(_prep7(x), train_mode, _scope="pose_encoder/encoder/")
+    sg = _segments
+    block_features = encoder(_prep7(x), train_mode, _scope="pose_encoder/encoder/", _segments=sg)
     x = block_features[-1]
     size = x.shape[1]
     conv_id = 1
     s = "pose_encoder/"
     for i in range(4):
         srcs = [x, block_features[-1 * (i + 1)]] if i > 0 else [x]
-        x = _cbr(ctx, srcs, s + "conv_%d_0" % conv_id, s + "b_norm_%d_0" % conv_id, train_mode)
-        x = _cbr(ctx, [x], s + "conv_%d_1" % conv_id, s + "b_norm_%d_1" % conv_id, train_mode)
+        x = _cbr(ctx, srcs, s + "conv_%d_0" % conv_id, s + "b_norm_%d_0" % conv_id, train_mode, segments=sg)
+        x = _cbr(ctx, [x], s + "conv_%d_1" % conv_id, s + "b_norm_%d_1" % conv_id, train_mode, segments=sg)
         if size == final_res:
             # 1x1 head: fp32 output (bf16 logits would move mu by up to 2.7e-3, SURVEY.md §7)
             x = E.conv_layer(ctx, [x], s + "conv_0/conv2d/kernel", s + "conv_0/conv2d/bias", 1, 1, 0, out_f32=True)
             break
-        x = _cbr(ctx, [x], s + "conv_%d_0" % (conv_id + 1), s + "b_norm_%d_0" % (conv_id + 1), train_mode)
-        x = _cbr(ctx, [x], s + "conv_%d_1" % (conv_id + 1), s + "b_norm_%d_1" % (conv_id + 1), train_mode, upsample=True)
+        x = _cbr(ctx, [x], s + "conv_%d_0" % (conv_id + 1), s + "b_norm_%d_0" % (conv_id + 1), train_mode, segments=sg)
+        x = _cbr(ctx, [x], s + "conv_%d_1" % (conv_id + 1), s + "b_norm_%d_1" % (conv_id + 1), train_mode, upsample=True, segments=sg)
         size = x.shape[1]
         conv_id += 2
         if filters >= 8:
@@ -205,6 +209,25 @@ def pose_encoder_with_maps(x, n_pts, train_mode, map_hw=(32, 32)):
     """pose_encoder + get_gaussian_maps(mu, map_hw) with ONE pass over the logits (fused K1 kernel)."""
     logits = pose_encoder_logits(x, n_pts, train_mode)
     return _keypoints(get_context(), logits, map_hw)
+
+
+def pose_encoder_pair_with_maps(im, future_im, n_pts, train_mode, map_hw=(32, 32)):
+    """pose_encoder(im) and pose_encoder(future_im) (detector_translator_model.py:166-167: the SAME variables, two calls,
+    each with its own batch-norm statistics and moving-average update) as ONE pass over [im; future_im]: every layer is a
+    single launch with per-segment statistics, which halves the launch count of the detector and doubles the tiles per
+    launch on its under-filled 16x16 / 32x32 layers.  Returns ((mu_cur, maps_cur), (mu_fut, maps_fut))."""
+    ctx = get_context()
+    B = im.shape[0]
+    logits = pose_encoder_logits(torch.cat([im, future_im], dim=0), n_pts, train_mode, _segments=2)
+    mu, maps = _keypoints(ctx, logits, map_hw)
+    cur_map, fut_map = maps[:B], maps[B:]
+    if ctx.tape is not None:
+        # the two halves receive their gradients separately (joint_embedding's backward): they are views of one buffer
+        d_maps = torch.empty_like(maps)
+        ctx.tape.set_grad(maps, d_maps)
+        ctx.tape.set_grad(cur_map, d_maps[:B])
+        ctx.tape.set_grad(fut_map, d_maps[B:])
+    return (mu[:B], cur_map), (mu[B:], fut_map)
 
 
 def joint_embedding(embedding, cur_map, fut_map):
@@ -308,7 +331,8 @@ def img_discr(x, need_input_grad=False):
     return E.conv_layer(ctx, [h], "img_discr/D_logit/conv2d/kernel", None, 3, 1, 1, out_f32=True)
 
 
-def maxpool(x):
+def maxpool(x, grad_rows=None):
+    """grad_rows=(lo, hi): only that run of images carries a gradient (see engine.conv_layer)."""
     ctx = get_context()
     y = ops.maxpool_fwd(x)
     if ctx.tape is not None:
@@ -319,6 +343,10 @@ def maxpool(x):
             if g is None:
                 return
             dx, acc = tape.acquire(x)
-            ops.maxpool_bwd(g, x, dx, relu_mask=False, accumulate=acc)
+            if grad_rows is None:
+                ops.maxpool_bwd(g, x, dx, relu_mask=False, accumulate=acc)
+            else:
+                lo, hi = grad_rows
+                ops.maxpool_bwd(g[lo:hi], x[lo:hi], dx[lo:hi], relu_mask=False, accumulate=acc)
         tape.record(bwd)
     return y

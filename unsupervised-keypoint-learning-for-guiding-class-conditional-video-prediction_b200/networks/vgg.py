@@ -38,13 +38,14 @@ def load_npy_into(ctx, vgg19_path):
 VGG_UNROLL = (3, 1, 16)   # conv1_1 as a 3x1 convolution over 3 horizontal taps x 3 channels (9 of 16 channels used)
 
 
-def prepare(x, prep):
+def prepare(x, prep, out=None):
     """float32 image -> W-unrolled bf16 VGG input (ops.image_prep_unrolled with `prep` = affine map + channel order)."""
-    return ops.image_prep_unrolled(x.contiguous(), VGG_UNROLL[0], VGG_UNROLL[1], VGG_UNROLL[2], prep)
+    return ops.image_prep_unrolled(x.contiguous(), VGG_UNROLL[0], VGG_UNROLL[1], VGG_UNROLL[2], prep, out=out)
 
 
-def features_from_prepared(xp, need_input_grad):
-    """xp: W-unrolled bf16 [N,H,W,16] in VGG input space (BGR minus mean), see prepare()."""
+def features_from_prepared(xp, need_input_grad, grad_rows=None):
+    """xp: W-unrolled bf16 [N,H,W,16] in VGG input space (BGR minus mean), see prepare().  grad_rows=(lo, hi): only those
+    images carry a gradient (the generated half of [gt; pred], reference :274-279)."""
     from . import maxpool
     ctx = _ctx()
     feats = []
@@ -52,11 +53,11 @@ def features_from_prepared(xp, need_input_grad):
     first = True
     for name in _ORDER:
         if name == "pool":
-            x = maxpool(x)
+            x = maxpool(x, grad_rows)
             continue
         x = E.conv_layer(ctx, [x], "vgg/%s/filter" % name, "vgg/%s/biases" % name, (3, 1) if first else 3, 1, 0,
                          act=tc.ACT_RELU, need_input_grad=(need_input_grad or not first),
-                         wshape=(3, 1, 9, 64) if first else None)
+                         wshape=(3, 1, 9, 64) if first else None, grad_rows=grad_rows)
         first = False
         if name in _TAPS:
             feats.append(x)

@@ -47,13 +47,16 @@ def image_prep_bwd(g, dx, prep=IDENT_PREP, accumulate=False):
     return dx
 
 
-def image_prep_unrolled(x, kw, pad_left, cpad, prep=IDENT_PREP):
+def image_prep_unrolled(x, kw, pad_left, cpad, prep=IDENT_PREP, out=None):
     """f32 [N,H,W,3] -> bf16 [N,H,W,cpad] with out[..., j*3+c] = prep(x[..., w+j-pad_left, c]) (zero outside): turns a
-    KHxKW first-layer convolution into a KHx1 one over KW*3 channels."""
+    KHxKW first-layer convolution into a KHx1 one over KW*3 channels.  `out`: optional destination (a batch slice of a
+    larger buffer)."""
     assert x.dtype == F32 and x.dim() == 4 and x.shape[-1] == 3 and x.is_cuda
     x = x.contiguous()
     N, H, W, _ = x.shape
-    out = torch.empty((N, H, W, cpad), device=x.device, dtype=BF16)
+    if out is None:
+        out = torch.empty((N, H, W, cpad), device=x.device, dtype=BF16)
+    assert out.is_contiguous() and tuple(out.shape) == (N, H, W, cpad) and out.dtype == BF16
     a, b, perm = prep
     _lib.call("kp_image_prep_unrolled", _p(x), N, H, W, int(kw), int(pad_left), int(cpad), _f3(a), _f3(b), _i3(perm), _p(out),
               _st())
@@ -81,15 +84,17 @@ def bn_finalize(ssum, ssq, bias, gamma, beta, count, moving_mean, moving_var, ep
 
 
 def bn_stats_apply(x, ssum, ssq, bias, gamma, beta, count, moving_mean, moving_var, relu=True, upsample=False, eps=1e-5,
-                   decay=0.999):
-    """bn_finalize + bn_act_apply in one launch -> (out, scale, shift, mean, rstd)."""
+                   decay=0.999, segments=1):
+    """bn_finalize + bn_act_apply in one launch -> (out, scale, shift, mean, rstd).  segments > 1: the batch is that many
+    equal runs of images normalised with their own statistics (ssum / ssq and the four returned vectors are
+    [segments*C]; `count` = pixels of ONE segment)."""
     N, H, W, C = x.shape
     dev = x.device
-    par = torch.empty((4, C), device=dev, dtype=F32)
+    par = torch.empty((4, segments * C), device=dev, dtype=F32)
     out = torch.empty((N, 2 * H, 2 * W, C) if upsample else (N, H, W, C), device=dev, dtype=BF16)
     _lib.call("kp_bn_stats_apply", _p(ssum), _p(ssq), _p(bias), _p(gamma), _p(beta), float(count), eps, decay,
               _p(moving_mean), _p(moving_var), _p(par[0]), _p(par[1]), _p(par[2]), _p(par[3]), _p(x), 1 if relu else 0,
-              1 if upsample else 0, N, H, W, C, _p(out), _st())
+              1 if upsample else 0, N, H, W, C, _p(out), segments, _st())
     return out, par[0], par[1], par[2], par[3]
 
 
@@ -102,15 +107,16 @@ def bn_act_apply(x, scale, shift, relu=True, upsample=False):
 
 
 def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False, gbeta_acc=None, ggamma_acc=None,
-               zeroed=None):
-    """`zeroed`: optional pre-zeroed f32 buffer of >= 2*C elements for this call's dbeta/dgamma sums (saves two
+               zeroed=None, segments=1):
+    """`zeroed`: optional pre-zeroed f32 buffer of >= 2*segments*C elements for this call's dbeta/dgamma sums (saves two
     memsets); gbeta_acc / ggamma_acc: parameter-gradient views that receive += dbeta / dgamma inside the kernel."""
     N, H, W, C = x.shape
+    SC = segments * C
     if zeroed is not None:
-        dbeta, dgamma, pre = zeroed[:C], zeroed[C:2 * C], 1
+        dbeta, dgamma, pre = zeroed[:SC], zeroed[SC:2 * SC], 1
     else:
-        dbeta = torch.empty(C, device=x.device, dtype=F32)
-        dgamma = torch.empty(C, device=x.device, dtype=F32)
+        dbeta = torch.empty(SC, device=x.device, dtype=F32)
+        dgamma = torch.empty(SC, device=x.device, dtype=F32)
         pre = 0
     dx = torch.empty_like(x)
     if upsample:
@@ -120,7 +126,7 @@ def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False, gbe
         _lib.call("kp_upsample2x_bwd", _p(dout), N, H, W, C, _p(dact), _st())
         dout = dact
     _lib.call("kp_bn_act_bwd", _p(dout), _p(x), _p(scale), _p(shift), _p(mean), _p(rstd), 1 if relu else 0,
-              0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _p(gbeta_acc), _p(ggamma_acc), pre, _st())
+              0, N, H, W, C, _p(dbeta), _p(dgamma), _p(dx), _p(gbeta_acc), _p(ggamma_acc), pre, segments, _st())
     return dx, dgamma, dbeta
 
 

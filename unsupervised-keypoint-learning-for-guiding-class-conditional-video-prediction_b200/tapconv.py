@@ -34,7 +34,8 @@ class TapConvDesc(ctypes.Structure):
                 ("out_sn", ctypes.c_longlong),
                 ("Cout", ctypes.c_int), ("out_f32", ctypes.c_int), ("act", ctypes.c_int), ("alpha", ctypes.c_float),
                 ("accumulate", ctypes.c_int),
-                ("TW", ctypes.c_int), ("TH", ctypes.c_int), ("TN", ctypes.c_int), ("BN", ctypes.c_int)]
+                ("TW", ctypes.c_int), ("TH", ctypes.c_int), ("TN", ctypes.c_int), ("BN", ctypes.c_int),
+                ("stat_groups", ctypes.c_int)]
 
 
 def same_pad(in_size, k, s):
@@ -80,7 +81,7 @@ class TapPlan:
         first = self.taps[0][2]
         return sum(-(-self.views[first + s]["C"] // self.CB) for s in range(self.n_src))
 
-    def desc(self, act=ACT_NONE, alpha=0.0, out_f32=False, cout_written=None, tile=None, bn=0, accumulate=False):
+    def desc(self, act=ACT_NONE, alpha=0.0, out_f32=False, cout_written=None, tile=None, bn=0, accumulate=False, stat_groups=1):
         d = TapConvDesc()
         d.N = self.N
         d.n_maps = len(self.views)
@@ -101,6 +102,7 @@ class TapPlan:
         if tile is not None:
             d.TW, d.TH, d.TN = tile
         d.BN = bn
+        d.stat_groups = stat_groups
         return d
 
 
