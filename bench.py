@@ -280,7 +280,7 @@ def run_reference(args):
 # GPU arms
 # --------------------------------------------------------------------------------------------------
 _RESULT_FD = None
-CONV_KERNELS = ("tapconv_kernel", "tapconv2_kernel", "haloconv_kernel", "halo2_kernel", "wgrad_kernel")
+CONV_KERNELS = ("tapconv_kernel", "tapconv2_kernel", "haloconv_kernel", "halo2_kernel", "wgrad_kernel", "wgrad2_kernel")
 RIDGE_FLOP_PER_BYTE = 247.0     # bf16 ridge of B200: below it a layer is HBM-bound
 
 

@@ -591,6 +591,55 @@ def test_tma_halo_kernel_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypat
             assert (got[0][:cout].double() - s_ref).abs().max().item() <= 2e-3 * (s_ref.abs().max().item() + ref.abs().sum(dim=(0, 1, 2)).max().item() * 1e-2)
             assert (got[1][:cout].double() - q_ref).abs().max().item() <= 2e-3 * q_ref.abs().max().item()
 
+WGRAD2_CASES = [
+    # (N,H,W,Cx,c0,cin_total,cout,k)  - every branch of csrc/conv_wgrad2.cu (halo-tile weight gradient)
+    (2, 32, 32, 128, 0, 128, 128, 3),      # two 64-channel slots per tap, 9 accumulators of 128 columns in 3 tap groups
+    (2, 32, 32, 256, 0, 256, 256, 3),      # two ci blocks x two co blocks
+    (2, 32, 32, 64, 0, 64, 64, 3),         # Cin 64: two taps of a kernel row per M=128 MMA (LBO = one pixel row)
+    (2, 32, 32, 32, 0, 32, 32, 3),         # Cin 32: a whole 3-wide kernel row per MMA, 64-byte swizzle
+    (2, 32, 32, 16, 0, 16, 16, 3),         # Cin 16: 32-byte swizzle
+    (3, 24, 20, 32, 0, 32, 16, 3),         # ragged H/W (zero-filled tile borders), Cout 16
+    (2, 64, 64, 32, 0, 32, 32, (7, 1)),    # 7x1 taps (W-unrolled first layer): one tap per MMA group
+    (2, 32, 32, 16, 0, 16, 64, (3, 1)),    # VGG conv1_1 layout
+    (2, 16, 16, 128, 0, 128, 64, 3),       # one tile row of tiles, BN 64
+    (2, 32, 32, 64, 64, 128, 32, 3),       # second source of a virtual concat: rows [64,128) of a 128-row kernel
+    (4, 128, 128, 64, 0, 64, 64, 3),       # 128x128 geometry, many pixel splits
+]
+
+
+@pytest.mark.parametrize("case", WGRAD2_CASES)
+def test_halo_weight_gradient_matches_oracle_and_tap_kernel(cuda_dev, case, monkeypatch):
+    """csrc/conv_wgrad2.cu against the fp64 oracle (autograd of tf_ops.conv2d on the same bf16 operands) and against the
+    per-tap kernel (csrc/conv_wgrad.cu, KP_WGRAD_HALO=0)."""
+    from kp_b200 import conv, tapconv as tc
+    N, H, W, Cx, c0, cin_total, cout, k = case
+    kh, kw = (k, k) if isinstance(k, int) else k
+    rng = np.random.default_rng(N * 100 + H + Cx + cout)
+    x = torch.from_numpy(rng.normal(size=(N, H, W, Cx)).astype(np.float32)).to(BF)
+    dy = torch.from_numpy(rng.normal(size=(N, H, W, cout)).astype(np.float32)).to(BF)
+    plan = tc.plan_conv_wgrad((N, H, W, Cx), k, 1, 0, cout, cin_slice=(c0, c0 + Cx, cin_total))
+    xd, dyd = x.to(cuda_dev), dy.to(cuda_dev)
+
+    def run(halo):
+        monkeypatch.setenv("KP_WGRAD_HALO", "2" if halo else "0")
+        dw = torch.zeros((kh, kw, cin_total, cout), device=cuda_dev)
+        conv.run_wgrad(plan, xd, dyd, dw)
+        torch.cuda.synchronize()
+        return dw.cpu()
+    got, old = run(True), run(False)
+    w64 = torch.zeros((kh, kw, Cx, cout), dtype=torch.float64, requires_grad=True)
+    y = T.conv2d(x.double(), w64, None, 1, 0)
+    y.backward(dy.double())
+    ref = torch.zeros((kh, kw, cin_total, cout), dtype=torch.float64)
+    ref[:, :, c0:c0 + Cx] = w64.grad
+    scale = ref.abs().max().item()
+    assert torch.isfinite(got).all()
+    assert (got.double() - ref).abs().max().item() <= 2e-3 * scale, (got.double() - ref).abs().max().item() / scale
+    assert (got - old).abs().max().item() <= 2e-3 * scale
+    untouched = torch.ones(cin_total, dtype=torch.bool)
+    untouched[c0:c0 + Cx] = False
+    assert got[:, :, untouched].abs().max().item() == 0.0 if untouched.any() else True
+
 
 @pytest.mark.parametrize("geom", [(2, 32, 32, 16, 32, 16, 3), (2, 16, 16, 64, 128, 64, 3), (3, 24, 20, 32, 64, 8, 1)])
 def test_two_layer_chain_forward_backward(cuda_dev, geom):

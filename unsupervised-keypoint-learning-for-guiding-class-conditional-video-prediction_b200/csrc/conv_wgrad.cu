@@ -214,6 +214,8 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
     KP_REQUIRE(d->n_maps >= 1 && d->n_maps <= KP_MAX_MAPS, "kp_wgrad: n_maps %d out of range", d->n_maps);
     KP_REQUIRE(d->n_taps >= 1 && d->n_taps <= KP_MAX_TAPS, "kp_wgrad: n_taps %d out of range", d->n_taps);
     KP_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cin > 0 && d->Cout > 0, "kp_wgrad: empty problem");
+    // stride-1 KHxKW layers: halo-tile kernel (X travels once per pixel tile instead of once per tap)
+    if (wgrad2_eligible(d)) return wgrad2_launch(d, x, dy, dw, st);
     WgradKParams p;
     memset(&p, 0, sizeof(p));
     // operand channel blocks follow the operands' own channel counts (desc->CB is only validated)

@@ -52,6 +52,9 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
 
 // conv_wgrad.cu
 int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
+// conv_wgrad2.cu (halo-tile weight gradient of the stride-1 layers)
+bool wgrad2_eligible(const kp_wgrad_desc* d);
+int wgrad2_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
 
 // elementwise.cu
 int ew_image_prep(const float* x, long long P, const float* a, const float* b, const int* perm, void* out, cudaStream_t st);
