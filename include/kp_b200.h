@@ -278,6 +278,13 @@ int kp_bce_logits_fwd_bwd(const float* logits, int n, float label, float weight,
  * lr_t_dev (nullable): device scalar holding a precomputed lr_t that overrides lr/t (CUDA-graph replays).     */
 int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                int t, float grad_scale, const float* lr_t_dev, void* stream);
+/* 1x1 convolution of a narrow bf16 activation into fp32: out[p][co] = bias[co] + sum_ci x[p][ci] * w[ci][co]
+ *   replaces: the detector head layers.conv(x, n_pts, kernel=1, stride=1) 'conv_0' (models/networks/__init__.py:57-59),
+ *             whose logits feed get_coord in fp32.  x bf16 [P,Cin] (Cin = 16), w f32 [Cin,Cout] (the HWIO kernel of a 1x1
+ *             convolution as stored; rounded to bf16 on load like every convolution weight of this library), bias f32 [Cout]
+ *             (nullable), out f32 [P,Cout], Cout a multiple of 4 up to 40.
+ *   HBM-bound (7 FLOP/B): CUDA-core FMAs, fully coalesced 16-byte stores through a shared-memory transpose.  */
+int kp_conv1x1_f32(const void* x, const float* w, const float* bias, long long P, int Cin, int Cout, float* out, void* stream);
 /* out[c] += sum over pixels of g bf16 [P,C] (bias gradients). */
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream);
 

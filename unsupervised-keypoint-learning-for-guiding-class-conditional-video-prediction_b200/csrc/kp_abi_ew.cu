@@ -145,6 +145,12 @@ int kp_pack_weights_batch(const void* jobs_dev, int n_jobs, int total_blocks, vo
     KP_NONNULL(jobs_dev);
     return ew_pack_weights_batch(jobs_dev, n_jobs, total_blocks, ST);
 }
+int kp_conv1x1_f32(const void* x, const float* w, const float* bias, long long P, int Cin, int Cout, float* out, void* stream) {
+    KP_NONNEG(P);
+    if (P == 0) return KP_OK;
+    KP_NONNULL(x); KP_NONNULL(w); KP_NONNULL(out);
+    return head1x1_launch(x, w, bias, P, Cin, Cout, out, ST);
+}
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream) {
     KP_NONNEG(P);
     if (P == 0) return KP_OK;

@@ -56,6 +56,9 @@ int wgrad_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* d
 bool wgrad2_eligible(const kp_wgrad_desc* d);
 int wgrad2_launch(const kp_wgrad_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st);
 
+// head1x1.cu
+int head1x1_launch(const void* x, const float* w, const float* bias, long long P, int Cin, int Cout, float* out, cudaStream_t st);
+
 // elementwise.cu
 int ew_image_prep(const float* x, long long P, const float* a, const float* b, const int* perm, void* out, cudaStream_t st);
 int ew_image_prep_bwd(const void* g, long long P, const float* a, const int* perm, int accumulate, float* dx, cudaStream_t st);

@@ -344,8 +344,15 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
         return out
 
     # plain conv + bias + activation in the epilogue
-    y = torch.empty((N, Ho, Wo, cout), device=dev, dtype=F32 if out_f32 else BF16)
-    cv.run_plan(fplan, srcs, wp, bias, y, act=act, alpha=alpha)
+    k_h, k_w = tc._khw(k)
+    if (out_f32 and act == tc.ACT_NONE and k_h == 1 and k_w == 1 and stride == 1 and pad == 0 and len(srcs) == 1
+            and shapes[0][3] == 16 and cin_real == 16 and len(wnames) == 1 and cout % 4 == 0 and cout <= 40 and wshape is None):
+        # HBM-bound 1x1 head (16 -> n_pts fp32 logits): dedicated kernel with coalesced fp32 stores (csrc/head1x1.cu); it reads
+        # the fp32 master weights in place and rounds them to bf16 on load, like the packed copies of the tensor-core path
+        y = ops.conv1x1_f32(srcs[0], w, ctx.p(bnames[0]) if bnames else None)
+    else:
+        y = torch.empty((N, Ho, Wo, cout), device=dev, dtype=F32 if out_f32 else BF16)
+        cv.run_plan(fplan, srcs, wp, bias, y, act=act, alpha=alpha)
     if ctx.trace is not None:
         ctx.trace.append(dict(scope=_scope_of(wnames[0]), kind="plain", out=y))
     if ctx.tape is not None:

@@ -130,6 +130,14 @@ def bn_act_bwd(dout, x, scale, shift, mean, rstd, relu=True, upsample=False, gbe
     return dx, dgamma, dbeta
 
 
+def conv1x1_f32(x, w, bias):
+    """x bf16 [..., Cin] (Cin = 16), w f32 [1,1,Cin,Cout] / [Cin,Cout], bias f32 [Cout] or None -> f32 [..., Cout]."""
+    cin, cout = w.shape[-2], w.shape[-1]
+    out = torch.empty(tuple(x.shape[:-1]) + (cout,), device=x.device, dtype=F32)
+    _lib.call("kp_conv1x1_f32", _p(x), _p(w), _p(bias), x.numel() // cin, cin, cout, _p(out), _st())
+    return out
+
+
 def act_mask_bwd(dy, y, alpha):
     g = torch.empty_like(y)
     _lib.call("kp_act_mask_bwd", _p(dy), _p(y), float(alpha), y.numel(), _p(g), _st())
