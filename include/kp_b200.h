@@ -126,7 +126,9 @@ typedef struct {
     int Cout;                                /* channels written per pixel */
     int out_f32;                             /* 0: bf16 output, 1: f32 output */
     int act; float alpha;
-    int accumulate;                          /* != 0: out += result instead of out = result */
+    int accumulate;                          /* 1: out += result instead of out = result; 2: f32 output that the CALLER has
+                                                zeroed and that takes atomic adds (lets long-K launches split K over CTAs,
+                                                also into strided views: stride-2 data gradients of img_discr) */
     int TW, TH, TN, BN;                      /* tile: TW*TH*TN == 128 pixels x BN channels; 0 = let the library choose */
     int stat_groups;                         /* batch-norm statistics per batch segment: images [g*N/G, (g+1)*N/G) accumulate
                                                 into stats_sum/stats_sq + g*Cout_pad (G = stat_groups, 0/1 = one segment).  Two

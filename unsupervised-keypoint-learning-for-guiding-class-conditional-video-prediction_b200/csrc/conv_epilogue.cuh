@@ -74,9 +74,21 @@ __device__ __forceinline__ void epi_chunk(const P& p, float (&v)[16], const int 
         if (valid && ch0 < p.Cout) {
             float* o = reinterpret_cast<float*>(p.out) + pix + ch0;
             const int nvalid = p.Cout - ch0;
+            if (ks == 0 && p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < nvalid) atomicAdd(o + j, v[j] + ((ks == 0 && p.bias != nullptr) ? s_bias[ch0 + j] : 0.f));
+                for (int j = 0; j < 16; ++j) v[j] += s_bias[ch0 + j];
+            }
+            if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                // vector reductions: 4 instead of 16 atomic operations per chunk
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                                 "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < nvalid) atomicAdd(o + j, v[j]);
+            }
         }
     } else if (valid && ch0 < p.Cout) {
         if (p.bias != nullptr) {

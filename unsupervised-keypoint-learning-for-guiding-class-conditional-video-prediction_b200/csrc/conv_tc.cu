@@ -437,12 +437,20 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
     if (TW <= 0 || TH <= 0 || TN <= 0)
         choose_pixel_tile(128, d->Wo, d->Ho, (d->stat_groups > 1 && ssum != nullptr) ? d->N / d->stat_groups : d->N, &TW, &TH, &TN);
     KP_REQUIRE(TW * TH * TN == 128, "kp_tapconv: tile %dx%dx%d is not 128 pixels", TW, TH, TN);
+    // Split-K needs an fp32 output that takes atomic adds: either a contiguous tensor this call may zero itself, or any
+    // view the CALLER has zeroed (accumulate == 2: the four strided parity views of a stride-2 data gradient).
+    const bool out_contiguous = d->out_off == 0 && d->out_sw == d->Cout && d->out_sh == (long long)d->Wo * d->Cout &&
+                                d->out_sn == (long long)d->Ho * d->Wo * d->Cout;
+    const bool splitk_ok = d->out_f32 && d->act == KP_ACT_NONE && ssum == nullptr &&
+                           (d->accumulate == 2 || (!d->accumulate && out_contiguous));
     if (BN <= 0) {
         BN = d->Cout_pad <= 256 ? d->Cout_pad : (d->Cout_pad % 256 == 0 ? 256 : 128);
         // Under-filled launches (few pixel tiles: 16x16 layers, img_discr conv_3..5): halve the channel tile until the
-        // tile count reaches ~the SM count; per-tile efficiency drops a little, idle SMs cost a lot.
+        // tile count reaches ~the SM count; per-tile efficiency drops a little, idle SMs cost a lot.  When the K loop is long
+        // and may be split over CTAs instead, the wide tile stays (every CTA then re-reads 4x less of the activations).
         const long long m_tiles = (long long)((d->Wo + TW - 1) / TW) * ((d->Ho + TH - 1) / TH) * ((d->N + TN - 1) / TN);
-        while (BN >= 128 && BN % 32 == 0 && m_tiles * (d->Cout_pad / BN) < (long long)(device_sm_count() * 3) / 4)
+        const bool prefer_splitk = splitk_ok && d->Ktot >= 32 * 64 && m_tiles * (d->Cout_pad / BN) * 2 <= device_sm_count();
+        while (!prefer_splitk && BN >= 128 && BN % 32 == 0 && m_tiles * (d->Cout_pad / BN) < (long long)(device_sm_count() * 3) / 4)
             BN /= 2;
         if (const char* e = getenv("KP_TAPCONV_BN_MAX")) {   // experiments: cap the channel tile
             const int cap = atoi(e);
@@ -507,16 +515,14 @@ int tapconv_launch(const kp_tapconv_desc* d, const void* const* src, const void*
         // no activation, contiguous output so that it can be zeroed here
         const int G = 64 / CB;
         const int n_groups = (total_iters + G - 1) / G;
-        const bool contiguous = d->out_off == 0 && d->out_sw == d->Cout && d->out_sh == (long long)d->Wo * d->Cout &&
-                                d->out_sn == (long long)d->Ho * d->Wo * d->Cout;
-        if (d->out_f32 && d->act == KP_ACT_NONE && !d->accumulate && ssum == nullptr && contiguous && n_groups >= 32 &&
-            p.total_tiles * 2 <= device_sm_count()) {
+        if (splitk_ok && n_groups >= 32 && p.total_tiles * 2 <= device_sm_count()) {
             int ks = device_sm_count() / p.total_tiles;
             if (ks > n_groups / 8) ks = n_groups / 8;
             if (ks > 1) {
                 p.groups_per_split = (n_groups + ks - 1) / ks;
                 p.ksplit = (n_groups + p.groups_per_split - 1) / p.groups_per_split;
-                KP_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)d->N * d->Ho * d->Wo * d->Cout * sizeof(float), st));
+                if (d->accumulate != 2)     // (accumulate == 2: the caller zeroed the whole output before its launches)
+                    KP_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)d->N * d->Ho * d->Wo * d->Cout * sizeof(float), st));
             }
         }
         if (p.ksplit == 1) p.groups_per_split = n_groups;

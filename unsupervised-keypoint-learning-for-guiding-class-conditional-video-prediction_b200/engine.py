@@ -424,6 +424,19 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
         C = shp[3]
         plans = ctx.plan("dgrad", (shp, k, stride, pad, cpad, c0, cin),
                          lambda shp=shp, c0=c0, C=C: tc.plan_conv_dgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
+        # Stride-2 data gradients of the deep, small-image layers (img_discr conv_3..5: a few hundred pixels, K = 4 taps x
+        # 512..2048 channels): skinny GEMMs that fill the machine only when K is split over CTAs.  They accumulate in fp32
+        # (atomic adds into a zeroed tensor shared by the four parity launches) and are cast to bf16 afterwards.
+        n_px = shp[0] * shp[1] * shp[2]
+        if (parents is None and stride == 2 and tape.grad(s) is None and n_px <= 128 * 64 and C % 8 == 0
+                and min(pl.Ktot for pl in plans) >= 2048):
+            tmp = torch.zeros(tuple(shp), device=ctx.device, dtype=F32)
+            for p in plans:
+                p.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
+                cv.run_plan(p, [dy], ctx.packed_weight("dgrad", wnames, p, w), None, tmp, accumulate=2)
+            tape.set_grad(s, ops.pack_channels([tmp], C))
+            c0 += C
+            continue
         if parents is None:
             dx, acc = tape.acquire(s)
         else:

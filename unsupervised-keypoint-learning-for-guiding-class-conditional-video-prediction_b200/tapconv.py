@@ -98,7 +98,7 @@ class TapPlan:
         d.Cout = self.rows if cout_written is None else cout_written
         d.out_f32 = 1 if out_f32 else 0
         d.act, d.alpha = act, alpha
-        d.accumulate = 1 if accumulate else 0
+        d.accumulate = int(accumulate) if accumulate in (0, 1, 2) else (1 if accumulate else 0)
         if tile is not None:
             d.TW, d.TH, d.TN = tile
         d.BN = bn
