@@ -35,7 +35,10 @@ def main():
     dev = torch.device("cuda:0")
     reps = int(os.environ.get("REPS", "10"))
     print("%-28s %10s %10s %8s   %s" % ("layer", "tap us", "halo us", "speedup", "TFLOP/s tap -> halo"))
+    only = os.environ.get("ONLY")
     for tag, N, H, W, cin, cout, k in LAYERS:
+        if only and only not in tag:
+            continue
         kh, kw = (k, k) if isinstance(k, int) else k
         x = torch.randn((N, H, W, cin), device=dev).to(torch.bfloat16)
         dy = torch.randn((N, H, W, cout), device=dev).to(torch.bfloat16)
