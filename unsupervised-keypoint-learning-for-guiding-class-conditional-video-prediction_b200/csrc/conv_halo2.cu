@@ -40,6 +40,8 @@ constexpr int H2_THREADS = 256;
 struct alignas(64) Halo2KParams {
     CUtensorMap mapA[KP_MAX_MAPS];
     CUtensorMap mapB;
+    CUtensorMap mapO;                                // fast epilogue: output store boxes {CW channels, 8, 4, 1}
+    int st_nbuf;                                     // staging sets per epilogue warp (1 or 2)
     int n_slots;
     int sl_kofs[H2_MAX_SLOTS];
     short sl_c0[H2_MAX_SLOTS], sl_nch[H2_MAX_SLOTS];
@@ -52,6 +54,7 @@ struct alignas(64) Halo2KParams {
     int NSA, NSB, halves, acc_bufs;
     uint32_t rcp_ntiles, rcp_tpi, rcp_tw;            // ceil(2^32/d): exact x/d for x*d < 2^32
     int TB, resident;
+    int t9;                                          // dense 3x3 taps at pitch 10: 1 forward order, 2 flipped (data gradient), 0 other
     int tiles_w, tiles_h, n_tiles, total_tiles;
     int Ho, Wo, N, BN, tmem_cols;
     int sgroups, group_n;                            // batch-norm statistics per batch segment of group_n images
@@ -84,7 +87,7 @@ __device__ __forceinline__ int h2_fdiv(int x, uint32_t rcp) { return rcp == 0u ?
 // MMA issue loop of ONE accumulator half (HF), run by a whole warp with one elected lane issuing.  A separate function
 // template per half keeps every operand provably warp-uniform for the compiler (anything derived from threadIdx would
 // be routed through vector registers and R2UR before each UTCHMMA).
-template <int HALVES, int KS, int HF>
+template <int HALVES, int KS, int HF, int T9>
 __device__ __forceinline__ void h2_issue(const Halo2KParams& p, const uint32_t tmem, const uint32_t smem_base, const uint32_t a_base,
                                          uint64_t* fullA, uint64_t* emptyA, uint64_t* fullB, uint64_t* emptyB, uint64_t* tfull,
                                          uint64_t* tempty) {
@@ -117,6 +120,28 @@ __device__ __forceinline__ void h2_issue(const Halo2KParams& p, const uint32_t t
             if (HF == 0 && leader && s == 0) KP_H2TRACE(3, lt);
             // low descriptor word: start address (16-byte units) | LBO field (unused for swizzled K-major: 1)
             const uint32_t a_lo0 = (((a_base + stA * p.a_slot_bytes) >> 4) + (uint32_t)HF * 16u * pitch * rb16) | (1u << 16);
+            if (T9) {
+                // resident weights + the dense 3x3 tap grid at pitch 10 (every 3x3 layer, forward or flipped): fully unrolled,
+                // tap offsets are immediates, one uniform multiply-add per tap and one add per operand per MMA
+                if (!b_ready) {
+                    mbar_wait(&fullB[0], 0);
+                    tc_fence_after();
+                    b_ready = true;
+                }
+                const uint32_t b_lo0 = ((smem_base >> 4) + (uint32_t)(s * 9) * b_box16) | (1u << 16);
+                const bool rev = p.t9 == 2;
+                const uint32_t a_org = rev ? a_lo0 + 22u * rb16 : a_lo0;
+                const int astep = rev ? -(int)rb16 : (int)rb16;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t a_lo = a_org + (uint32_t)(astep * ((t / 3) * 10 + (t % 3)));
+                    const uint32_t b_lo = b_lo0 + (uint32_t)t * b_box16;
+#pragma unroll
+                    for (int kk = 0; kk < (KS > 0 ? KS : 1); ++kk)
+                        umma_bf16_if_split(leader, d0, a_lo + 2u * kk, a_hi, b_lo + 2u * kk, b_hi, idesc, (t | kk) == 0 ? accum : 1u);
+                }
+                accum = 1u;
+            } else
             for (int t0 = 0; t0 < n_taps; t0 += TB) {
                 uint32_t stB = 0, b_lo;
                 if (resident) {
@@ -159,17 +184,20 @@ __device__ __forceinline__ void h2_issue(const Halo2KParams& p, const uint32_t t
 }
 
 // KS: K steps (16 channels each) per slot when all slots are alike (1, 2, 4), 0 = per slot.
-// EPI: 0 = general epilogue (epi_chunk), 1 = fast epilogue (epi_chunk_fast), 2 = fast epilogue + batch-norm statistics.
-template <int HALVES, int KS, int EPI>
+// EPI: 0 = general epilogue (epi_chunk); fast epilogues (TMA store): 1 = bias + activation, 2 = bias + batch-norm statistics,
+// 3 / 4 = the same with the statistics accumulated in registers (BN = 16 / 32).
+// T9: 1 = the unrolled 3x3 issue loop (resident weights, see h2_issue).
+template <int HALVES, int KS, int EPI, int T9>
 __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_constant__ Halo2KParams p) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* base = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    // [B region (1024-aligned)] [A slots (1024-aligned each)] [barriers] [tmem slot] [bias] [stats]
+    // [B region (1024-aligned)] [A slots (1024-aligned each)] [store staging (fast epilogue)] [barriers] [tmem slot] [bias] [stats]
     const uint32_t b_region = p.resident ? (((uint32_t)(p.n_slots * p.n_taps) * p.b_bytes + 1023u) & ~1023u)
                                          : (uint32_t)p.NSB * p.b_stage_bytes;
     const uint32_t a_base = smem_base + b_region;
-    uint64_t* fullA = reinterpret_cast<uint64_t*>(base + (size_t)b_region + (size_t)p.NSA * p.a_slot_bytes);
+    const uint32_t stage_bytes = EPI != 0 ? 4u * (uint32_t)p.st_nbuf * HALVES * 32u * (uint32_t)(p.BN < 64 ? p.BN : 64) * 2u : 0u;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(base + (size_t)b_region + (size_t)p.NSA * p.a_slot_bytes + stage_bytes);
     uint64_t* emptyA = fullA + p.NSA;
     uint64_t* fullB = emptyA + p.NSA;
     uint64_t* emptyB = fullB + p.NSB;
@@ -261,9 +289,9 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
         // is what bounds the short-K layers (an N <= 64 MMA occupies the tensor pipe for 8-32 cycles, one thread issues one
         // per ~40 cycles at best), hence: two issuing warps, K steps per slot as a template parameter (no branches between
         // MMAs), descriptors kept as (lo, hi) halves so that a step is one uniform add per operand.
-        h2_issue<HALVES, KS, 0>(p, tmem, smem_base, a_base, fullA, emptyA, fullB, emptyB, tfull, tempty);
+        h2_issue<HALVES, KS, 0, T9>(p, tmem, smem_base, a_base, fullA, emptyA, fullB, emptyB, tfull, tempty);
     } else if (warp == 3) {
-        if (HALVES == 2) h2_issue<HALVES, KS, 1>(p, tmem, smem_base, a_base, fullA, emptyA, fullB, emptyB, tfull, tempty);
+        if (HALVES == 2) h2_issue<HALVES, KS, 1, T9>(p, tmem, smem_base, a_base, fullA, emptyA, fullB, emptyB, tfull, tempty);
     } else if (warp >= 4) {
         // ------------------------------- epilogue -------------------------------
         const int q = warp & 3;                   // TMEM lane quarter of this warp
@@ -277,62 +305,162 @@ __global__ void __launch_bounds__(H2_THREADS, 2) halo2_kernel(const __grid_const
         float* const s_stat_w0 = s_stat + (warp - 4) * p.sgroups * 2 * p.cout_pad;
         const int group_n = p.group_n, gstride = 2 * p.cout_pad;
         if (EPI != 0) {
-            // fast epilogue: everything that is constant for the launch sits in registers, the chunk is branch-free
+            // fast epilogue: everything that is constant for the launch sits in registers, the chunk is branch-free.
+            // The bf16 tile leaves through shared memory: each warp stages its 4 x 8 pixels of both halves, CW = min(BN, 64)
+            // channels at a time, in the swizzled layout of a TMA box {CW, 8, 4, 1} (conflict-free 16-byte writes) and one
+            // lane stores the boxes.  A direct store would touch 32 different 128-byte lines per warp instruction (a pixel
+            // per thread) and the epilogue, not the tensor pipe, bounded every layer with <= 64 output channels.
             const EpiFast ef = {p.slope, p.cout_pad};
-            __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_off;
-            const long long out_sn = p.out_sn, out_sh = p.out_sh, out_sw = p.out_sw;
             const int Ho = p.Ho, Wo = p.Wo, BN = p.BN, n_tiles = p.n_tiles, tiles_w = p.tiles_w, acc_bufs = p.acc_bufs;
             const uint32_t rcp_ntiles = p.rcp_ntiles, rcp_tpi = p.rcp_tpi, rcp_tw = p.rcp_tw;
             const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+            const int CW = BN < 64 ? BN : 64;
+            const uint32_t rb = (uint32_t)CW * 2u, unit = 32u * rb, set_bytes = HALVES * unit;
+            const uint32_t nbuf = (uint32_t)p.st_nbuf;
+            const uint32_t stage_w = a_base + (uint32_t)p.NSA * p.a_slot_bytes + (uint32_t)(warp - 4) * nbuf * set_bytes;
+            // 16-byte piece j of staging row `lane` sits at piece j ^ swz (SWIZZLE_128B / 64B / 32B of the row width)
+            const uint32_t swz = rb == 128u ? (uint32_t)(lane & 7) : rb == 64u ? (uint32_t)((lane >> 1) & 3) : (uint32_t)((lane >> 2) & 1);
+            const uint32_t row_addr = (uint32_t)lane * rb;
+            uint32_t sbuf = 0;
+            // Batch-norm statistics.  EPI 2: one transpose-reduce per 16-column chunk (epi_stats16).  EPI 3/4 (BN = 16/32, one
+            // channel tile): every thread keeps running sums of its pixels' columns in registers across ALL its tiles and the
+            // transpose-reduce happens once per CTA (and when the tiles move to the next statistics segment): 4 packed
+            // operations per column pair and tile instead of ~170 instructions per chunk.
+            constexpr int SRN = EPI == 3 ? 1 : EPI == 4 ? 2 : 0;
+            constexpr bool STATS = EPI >= 2;
+            float2 as2[SRN > 0 ? SRN : 1][8], aq2[SRN > 0 ? SRN : 1][8];
+#pragma unroll
+            for (int ci = 0; ci < (SRN > 0 ? SRN : 1); ++ci)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) as2[ci][j] = aq2[ci][j] = make_float2(0.f, 0.f);
+            int cur_seg = -1;
             int lt = 0;
-            for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x, ++lt) {
+            for (int work = blockIdx.x;; work += gridDim.x, ++lt) {
+                const bool more = work < p.total_tiles;
                 const int mt = h2_fdiv(work, rcp_ntiles), nt = work - mt * n_tiles;
                 const int n = h2_fdiv(mt, rcp_tpi), r = mt - n * tiles_per_image;
+                if (SRN > 0) {
+                    const int seg = more ? n / group_n : -2;
+                    if (seg != cur_seg) {
+                        if (cur_seg >= 0) {
+                            float* const sw = s_stat_w0 + cur_seg * gstride;
+#pragma unroll
+                            for (int ci = 0; ci < SRN; ++ci) {
+                                float sv[16], qv[16];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    sv[2 * j] = as2[ci][j].x; sv[2 * j + 1] = as2[ci][j].y;
+                                    qv[2 * j] = aq2[ci][j].x; qv[2 * j + 1] = aq2[ci][j].y;
+                                    as2[ci][j] = aq2[ci][j] = make_float2(0.f, 0.f);
+                                }
+                                const float s1 = warp_colsum16(sv, lane), s2 = warp_colsum16(qv, lane);
+                                if ((lane & 1) == 0) {
+                                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                                    sw[ci * 16 + col] += s1;
+                                    sw[ef.cout_pad + ci * 16 + col] += s2;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        cur_seg = seg;
+                    }
+                }
+                if (!more) break;
                 const int tr = h2_fdiv(r, rcp_tw);
                 const int h0 = tr * TILE_ROWS, w0 = (r - tr * tiles_w) * 8;
                 const int n_off = nt * BN;
                 const int acc = acc_bufs == 2 ? (lt & 1) : 0;
-                const int uw = w0 + tw;
                 float* const s_stat_w = s_stat_w0 + (n / group_n) * gstride;       // this image's statistics segment
-                __nv_bfloat16* const o_n = outp + (long long)n * out_sn + (long long)uw * out_sw + n_off;
                 if (et == 0) KP_H2TRACE(5, lt);
                 mbar_wait(&tfull[acc], (lt / acc_bufs) & 1);
                 tc_fence_after();
                 if (et == 0) KP_H2TRACE(6, lt);
-                // chunk-major: the same 16 columns of both accumulator halves are in registers together, so the batch-norm
-                // statistics need ONE transpose-reduce per statistic per chunk for the whole 256-pixel tile
+                // chunk-major: the same 16 columns of both accumulator halves are in registers together
+                const bool edge = (h0 + TILE_ROWS > Ho) || (w0 + 8 > Wo);      // warp-uniform: the tile overhangs the image
                 bool valid[HALVES];
-                __nv_bfloat16* o_p[HALVES];
 #pragma unroll
-                for (int hf = 0; hf < HALVES; ++hf) {
-                    const int uh = h0 + hf * 16 + th;
-                    valid[hf] = (uh < Ho) && (uw < Wo);
-                    o_p[hf] = o_n + (long long)uh * out_sh;
-                }
+                for (int hf = 0; hf < HALVES; ++hf) valid[hf] = (h0 + hf * 16 + th < Ho) && (w0 + tw < Wo);
                 const uint32_t t_row = t_lane + (uint32_t)(acc * HALVES * BN);
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                auto chunk = [&](const int c0, const int ci) {
                     float v[HALVES][16];
+                    if (HALVES == 2) {
+                        // both halves' loads in flight before the first use
+                        uint32_t r0[16], r1[16];
+                        tmem_ld16_issue(t_row + (uint32_t)c0, r0);
+                        tmem_ld16_issue(t_row + (uint32_t)(BN + c0), r1);
+                        tmem_ld_wait2(r0, r1);
 #pragma unroll
-                    for (int hf = 0; hf < HALVES; ++hf) tmem_ld16(t_row + (uint32_t)(hf * BN + c0), v[hf]);
+                        for (int j = 0; j < 16; ++j) {
+                            v[0][j] = __uint_as_float(r0[j]);
+                            v[HALVES - 1][j] = __uint_as_float(r1[j]);
+                        }
+                    } else {
+                        tmem_ld16(t_row + (uint32_t)c0, v[0]);
+                    }
                     if (c0 + 16 >= BN) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
-                    if (EPI == 2) {
-#pragma unroll
-                        for (int hf = 0; hf < HALVES; ++hf)
-                            if (!valid[hf]) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[hf][j] = 0.f;
-                            }
-                        epi_stats16<HALVES>(v, lane, s_stat_w + n_off + c0, ef.cout_pad);
+                    const int cl = c0 & (CW - 1);                  // channel inside the current store box
+                    if (cl == 0) {
+                        // the staging set about to be rewritten: its previous store must have read it
+                        if (lane == 0) {
+                            if (nbuf == 2u) bulk_wait_group_read<1>();
+                            else bulk_wait_group_read<0>();
+                        }
+                        __syncwarp();
                     }
+                    const uint32_t set = stage_w + sbuf * set_bytes + row_addr;
+                    const uint32_t pc = (uint32_t)(cl >> 3);
 #pragma unroll
-                    for (int hf = 0; hf < HALVES; ++hf) epi_chunk_fast(v[hf], valid[hf], o_p[hf] + c0, s_bias + n_off + c0, ef);
+                    for (int hf = 0; hf < HALVES; ++hf)
+                        epi_chunk_fast_smem<!STATS>(v[hf], set + hf * unit + ((pc ^ swz) << 4), set + hf * unit + (((pc + 1u) ^ swz) << 4),
+                                                    s_bias + n_off + c0, ef);
+                    if (cl + 16 == CW) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll
+                            for (int hf = 0; hf < HALVES; ++hf)
+                                tma_store_4d(&p.mapO, stage_w + sbuf * set_bytes + hf * unit, n_off + c0 - cl, w0, h0 + hf * 16 + q * 4, n);
+                            bulk_commit_group();
+                        }
+                        sbuf ^= nbuf - 1u;
+                    }
+                    if (STATS) {
+                        // an output pixel outside the image still saw real halo pixels: keep it out of the statistics
+                        if (edge) {
+#pragma unroll
+                            for (int hf = 0; hf < HALVES; ++hf)
+                                if (!valid[hf]) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[hf][j] = 0.f;
+                                }
+                        }
+                        if (SRN > 0) {
+#pragma unroll
+                            for (int hf = 0; hf < HALVES; ++hf)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float2 x = make_float2(v[hf][2 * j], v[hf][2 * j + 1]);
+                                    as2[ci][j] = __fadd2_rn(as2[ci][j], x);
+                                    aq2[ci][j] = __ffma2_rn(x, x, aq2[ci][j]);
+                                }
+                        } else {
+                            epi_stats16<HALVES>(v, lane, s_stat_w + n_off + c0, ef.cout_pad);
+                        }
+                    }
+                };
+                if (SRN > 0) {
+#pragma unroll
+                    for (int ci = 0; ci < SRN; ++ci) chunk(ci * 16, ci);
+                } else {
+                    for (int c0 = 0; c0 < BN; c0 += 16) chunk(c0, 0);
                 }
                 if (et == 0) KP_H2TRACE(7, lt);
             }
+            if (lane == 0) bulk_wait_group<0>();       // the stores read shared memory: keep the CTA alive until they are done
         } else {
             int lt = 0;
             for (int work = blockIdx.x; work < p.total_tiles; work += gridDim.x, ++lt) {
@@ -536,14 +664,28 @@ int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* w
     const uint32_t epi_bytes = (ssum != nullptr ? 1u + 8u * (uint32_t)G : 1u) * (uint32_t)d->Cout_pad * sizeof(float);
     const uint32_t all_b = (uint32_t)(ns * d->n_taps) * p.b_bytes;
     const uint32_t fixed = epi_bytes + 1024u + 512u;
+    // statistics together with an activation (no layer of the stage-1 graph) take the general epilogue
+    const bool fast = epi_fast_ok(d, out, 1) && !(ssum != nullptr && d->act != KP_ACT_NONE);
+    // fast epilogue: store staging, per epilogue warp st_nbuf sets of [halves][32 pixels][CW channels] bf16.  Two sets
+    // (a store in flight while the next box is written) when the CTA owns the SM and the boxes are small.
+    const uint32_t CW = BN < 64 ? (uint32_t)BN : 64u;
+    auto nbuf_of = [&](bool two_) {
+        if (const char* e = getenv("KP_HALO2_STAGE_NBUF")) return atoi(e) >= 2 ? 2u : 1u;
+        return (two_ || BN > 64) ? 1u : 2u;
+    };
+    bool one_set = false;                              // two sets did not fit: fall back to one
+    auto budget_of = [&](bool two_) {
+        const uint32_t stage = fast ? 4u * (one_set ? 1u : nbuf_of(two_)) * (uint32_t)p.halves * 32u * CW * 2u : 0u;
+        return (two_ ? 111u : 222u) * 1024u - fixed - stage;
+    };
     // Two CTAs per SM whenever one CTA fits half of the SM's shared memory and TMEM: two independent TMA / issue /
     // epilogue pipelines per SM for the short-K layers.
     bool two = p.tmem_cols <= 256;
-    uint32_t budget = (two ? 111u : 222u) * 1024u - fixed;
+    uint32_t budget = budget_of(two);
     p.resident = (p.n_tiles == 1 && all_b <= (two ? 56u : 100u) * 1024u) ? 1 : 0;
     if (two && !p.resident && p.n_tiles == 1 && all_b <= 100u * 1024u) {      // resident weights beat a second CTA
         two = false;
-        budget = 222u * 1024u - fixed;
+        budget = budget_of(false);
         p.resident = 1;
     }
     if (const char* e = getenv("KP_HALO_RESIDENT")) if (atoi(e) == 0) p.resident = 0;
@@ -570,9 +712,15 @@ int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* w
         }
         const bool fits = p.NSA >= 2 && p.NSB >= 1 && (p.resident || p.NSB >= 2);
         if (fits) break;
+        if (fast && !one_set && nbuf_of(two) == 2u) {
+            one_set = true;
+            budget = budget_of(two);
+            --attempt;
+            continue;
+        }
         KP_REQUIRE(two && attempt == 0, "kp_tapconv(halo2): tile does not fit shared memory");
         two = false;                                   // retry with the whole SM
-        budget = 222u * 1024u - fixed;
+        budget = budget_of(false);
     }
     {
         KP_REQUIRE((reinterpret_cast<uintptr_t>(wpacked) & 15) == 0, "kp_tapconv(halo2): packed weights not 16-byte aligned");
@@ -600,10 +748,29 @@ int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* w
     p.Cout = d->Cout; p.cout_pad = d->Cout_pad; p.out_f32 = d->out_f32; p.act = d->act; p.alpha = d->alpha;
     p.accumulate = d->accumulate; p.ksplit = 1;
     p.bias = bias; p.ssum = ssum; p.ssq = ssq;
-    const bool fast = epi_fast_ok(d, out, 1);
     p.slope = epi_fast_slope(d);
+    p.st_nbuf = one_set ? 1 : (int)nbuf_of(two);
+    const uint32_t stage_bytes = fast ? 4u * (uint32_t)p.st_nbuf * (uint32_t)p.halves * 32u * CW * 2u : 0u;
+    if (fast) {
+        // epi_fast_ok: bf16 output, Cout == Cout_pad (multiple of 16), view offset and strides multiples of 8 elements
+        cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
+        cuuint64_t gstr[3] = {(cuuint64_t)d->out_sw * 2, (cuuint64_t)d->out_sh * 2, (cuuint64_t)d->out_sn * 2};
+        cuuint32_t box[4] = {CW, 8u, 4u, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUtensorMapSwizzle swz = CW == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CW == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        CUresult r = encode(&p.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<char*>(out) + d->out_off * 2, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("kp_tapconv(halo2): cuTensorMapEncodeTiled(output) failed with %d (C=%d W=%d H=%d N=%d strides %lld,%lld,%lld)", (int)r,
+                      d->Cout, d->Wo, d->Ho, d->N, (long long)d->out_sw, (long long)d->out_sh, (long long)d->out_sn);
+            return KP_ERR_DRIVER;
+        }
+    } else {
+        p.mapO = p.mapB;
+    }
 
-    size_t smem = (size_t)b_region + (size_t)p.NSA * p.a_slot_bytes + (size_t)(2 * p.NSA + 2 * p.NSB + 4) * 8 + 16 + epi_bytes + 1024;
+    size_t smem = (size_t)b_region + (size_t)p.NSA * p.a_slot_bytes + stage_bytes + (size_t)(2 * p.NSA + 2 * p.NSB + 4) * 8 + 16 + epi_bytes +
+                  1024;
     // a CTA that needs more than half of the TMEM columns must not share its SM (the second allocation would block)
     if (!two && smem < 116u * 1024u) smem = 116u * 1024u;
     KP_REQUIRE(smem <= 227u * 1024u, "kp_tapconv(halo2): shared memory %zu exceeds the SM", smem);
@@ -621,27 +788,48 @@ int halo2_launch(const kp_tapconv_desc* d, const void* const* src, const void* w
     for (int s = 1; s < ns; ++s)
         if (p.sl_nch[s] != p.sl_nch[0]) ks = 0;
     if (ks != 1 && ks != 2 && ks != 4) ks = 0;
-    const int epi = !fast ? 0 : (ssum != nullptr ? 2 : 1);
+    // fast epilogues: 1 = bias + activation, 2..4 = bias + batch-norm statistics (no activation; 3/4 = register-accumulated
+    // for BN 16/32 with both halves)
+    int epi = !fast ? 0 : ssum == nullptr ? 1 : 2;
+    if (epi == 2 && p.halves == 2 && p.n_tiles == 1 && (BN == 16 || BN == 32) && !getenv("KP_HALO2_NO_STATREG")) epi = BN == 16 ? 3 : 4;
     if (epi == 0) ks = 0;                            // the general epilogue is only instantiated with the general issue loop
+    // dense 3x3 tap grid at pitch 10 in forward or flipped order + resident weights: unrolled issue loop
+    p.t9 = 0;
+    if (d->n_taps == 9 && p.pitch == 10 && p.resident && ks > 0 && p.halves == 2 && !getenv("KP_HALO2_NO_T9")) {
+        bool fwd = true, rev = true;
+        for (int t = 0; t < 9; ++t) {
+            const int f = (t / 3) * 10 + t % 3;
+            fwd = fwd && p.tapoff[t] == f;
+            rev = rev && p.tapoff[t] == 22 - f;
+        }
+        p.t9 = fwd ? 1 : rev ? 2 : 0;
+    }
+    const int t9 = p.t9 != 0 ? 1 : 0;
     typedef void (*KernelFn)(const Halo2KParams);
     KernelFn fnk = nullptr;
-#define KP_H2_PICK(H, K, E) if (p.halves == H && ks == K && epi == E) fnk = halo2_kernel<H, K, E>
-    KP_H2_PICK(1, 0, 0); KP_H2_PICK(2, 0, 0);
-    KP_H2_PICK(1, 0, 1); KP_H2_PICK(1, 1, 1); KP_H2_PICK(1, 2, 1); KP_H2_PICK(1, 4, 1);
-    KP_H2_PICK(1, 0, 2); KP_H2_PICK(1, 1, 2); KP_H2_PICK(1, 2, 2); KP_H2_PICK(1, 4, 2);
-    KP_H2_PICK(2, 0, 1); KP_H2_PICK(2, 1, 1); KP_H2_PICK(2, 2, 1); KP_H2_PICK(2, 4, 1);
-    KP_H2_PICK(2, 0, 2); KP_H2_PICK(2, 1, 2); KP_H2_PICK(2, 2, 2); KP_H2_PICK(2, 4, 2);
+#define KP_H2_PICK(H, K, E, T) if (p.halves == H && ks == K && epi == E && t9 == T) fnk = halo2_kernel<H, K, E, T>
+    KP_H2_PICK(1, 0, 0, 0); KP_H2_PICK(2, 0, 0, 0);
+    KP_H2_PICK(1, 0, 1, 0); KP_H2_PICK(1, 1, 1, 0); KP_H2_PICK(1, 2, 1, 0); KP_H2_PICK(1, 4, 1, 0);
+    KP_H2_PICK(1, 0, 2, 0); KP_H2_PICK(1, 1, 2, 0); KP_H2_PICK(1, 2, 2, 0); KP_H2_PICK(1, 4, 2, 0);
+    KP_H2_PICK(2, 0, 1, 0); KP_H2_PICK(2, 1, 1, 0); KP_H2_PICK(2, 2, 1, 0); KP_H2_PICK(2, 4, 1, 0);
+    KP_H2_PICK(2, 0, 2, 0); KP_H2_PICK(2, 1, 2, 0); KP_H2_PICK(2, 2, 2, 0); KP_H2_PICK(2, 4, 2, 0);
+    KP_H2_PICK(2, 1, 1, 1); KP_H2_PICK(2, 2, 1, 1); KP_H2_PICK(2, 4, 1, 1);
+    KP_H2_PICK(2, 1, 2, 1); KP_H2_PICK(2, 2, 2, 1); KP_H2_PICK(2, 4, 2, 1);
+    KP_H2_PICK(2, 0, 3, 0); KP_H2_PICK(2, 1, 3, 0); KP_H2_PICK(2, 2, 3, 0); KP_H2_PICK(2, 4, 3, 0);
+    KP_H2_PICK(2, 0, 4, 0); KP_H2_PICK(2, 1, 4, 0); KP_H2_PICK(2, 2, 4, 0); KP_H2_PICK(2, 4, 4, 0);
+    KP_H2_PICK(2, 1, 3, 1); KP_H2_PICK(2, 2, 3, 1); KP_H2_PICK(2, 4, 3, 1);
+    KP_H2_PICK(2, 1, 4, 1); KP_H2_PICK(2, 2, 4, 1); KP_H2_PICK(2, 4, 4, 1);
 #undef KP_H2_PICK
-    KP_REQUIRE(fnk != nullptr, "kp_tapconv(halo2): no kernel variant for halves=%d ks=%d epi=%d", p.halves, ks, epi);
+    KP_REQUIRE(fnk != nullptr, "kp_tapconv(halo2): no kernel variant for halves=%d ks=%d epi=%d t9=%d", p.halves, ks, epi, t9);
     {
         // once per variant: allow the full shared memory
-        static KernelFn done[32];
+        static KernelFn done[64];
         static int n_done = 0;
         bool seen = false;
         for (int i = 0; i < n_done; ++i) seen = seen || done[i] == fnk;
         if (!seen) {
             KP_CUDA_CHECK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fnk), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            if (n_done < 32) done[n_done++] = fnk;
+            if (n_done < 64) done[n_done++] = fnk;
         }
     }
     KP_CUDA_CHECK(launch_pdl(fnk, dim3(grid), dim3(H2_THREADS), smem, st, p));
