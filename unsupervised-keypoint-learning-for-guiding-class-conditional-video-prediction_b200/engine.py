@@ -68,9 +68,12 @@ class Tape:
         self.ops = []
         self.g = {}
         self.keep = []
+        self.joins = []          # contexts whose weight-gradient stream this backward pass forked (joined at its end)
+        self.branch = None       # stream of a forward branch: closures recorded while it is current run on it again
 
     def record(self, fn):
-        self.ops.append(fn)
+        on_branch = self.branch is not None and torch.cuda.current_stream() == self.branch
+        self.ops.append((fn, self.branch if on_branch else None))
 
     def grad(self, t):
         return self.g.get(id(t))
@@ -90,8 +93,15 @@ class Tape:
         return buf, False
 
     def backward(self):
-        for fn in reversed(self.ops):
-            fn()
+        for fn, st in reversed(self.ops):
+            if st is None:
+                fn()
+            else:
+                with torch.cuda.stream(st):
+                    fn()
+        for c in self.joins:
+            c.join_wgrad()
+        self.joins.clear()
         self.ops.clear()
         self.g.clear()
         self.keep.clear()
@@ -116,6 +126,13 @@ class Context:
         self.trace = None                             # list of dicts, one per stored tensor in call order (tests only)
         self.zpool = None
         self.zoff = 0
+        # Weight gradients on their own stream (set by the model): in the backward pass a layer's weight gradient depends
+        # only on (saved input, dy) and nobody needs it before the optimizer, so it runs beside the data-gradient chain
+        # (next layer's BN backward = HBM-bound, data gradient = tensor-bound) and fills the tails of those launches.
+        self.wgrad_stream = None
+        self.branch_stream = None     # independent sub-network (image_encoder beside pose_encoder), see Context.branch()
+        self._wg_keep = []            # (dy, inputs) kept alive until the join: the side stream still reads them
+        self._wg_pending = False
         self._plans = {}
         self._packed = {}
         self._jobs = {}        # id(group) -> [(key, plan, fp32 kernel view, packed bf16 tensor)]: re-packed in ONE launch
@@ -149,6 +166,28 @@ class Context:
         out = self.zpool[self.zoff:self.zoff + n]
         self.zoff += n4
         return out
+
+    def branch(self):
+        """Context manager: run an independent sub-network on the branch stream, forward and (through the tape) backward.
+        Usage: `with ctx.branch(): y = net(x)` ... independent work on the current stream ... `ctx.branch_join()`."""
+        return _Branch(self)
+
+    def branch_join(self):
+        br, tape = self.branch_stream, self.tape
+        if br is None:
+            return
+        torch.cuda.current_stream().wait_stream(br)
+        if tape is not None:
+            # backward: the branch's closures (recorded before this point) start after the gradients produced so far
+            tape.record(lambda: br.wait_stream(torch.cuda.current_stream()))
+
+    def join_wgrad(self, waiter=None):
+        """Make `waiter` (default: the current stream) wait for the weight gradients launched so far."""
+        if self._wg_pending:
+            (waiter or torch.cuda.current_stream()).wait_stream(self.wgrad_stream)
+            if waiter is None:
+                self._wg_pending = False
+                self._wg_keep.clear()
 
     # ---- parameter lookup ----
     def group_of(self, name):
@@ -235,6 +274,31 @@ class Context:
 # --------------------------------------------------------------------------------------------------
 # convolution layer (+ BN / activation), forward and tape entry
 # --------------------------------------------------------------------------------------------------
+class _Branch:
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.cm = None
+
+    def __enter__(self):
+        ctx = self.ctx
+        br, tape = ctx.branch_stream, ctx.tape
+        if br is None:
+            return self
+        br.wait_stream(torch.cuda.current_stream())
+        if tape is not None:
+            tape.branch = br
+            # backward: runs after the branch's closures were issued -> the main chain waits for them here
+            tape.record(lambda: torch.cuda.current_stream().wait_stream(br))
+        self.cm = torch.cuda.stream(br)
+        self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+        return False
+
+
 def _conv_weights(ctx, wnames, wshape=None):
     """HWIO kernel of the layer; several TF variables may be fused along Cout (translator heads).  `wshape`
     reinterprets the (contiguous) variable in place, e.g. [7,7,3,32] as [7,1,21,32] for the W-unrolled first layer."""
@@ -379,6 +443,39 @@ def conv_layer(ctx, srcs, wnames, bnames, k, stride, pad, *, bn=None, train_mode
     return y
 
 
+def _weight_grads(ctx, srcs, shapes, wnames, bnames, k, stride, pad, cout, dy, group, cin_real, wshape, cin, cpad):
+    """Weight and bias gradients of one convolution (accumulated into the group's flat gradient buffer)."""
+    k_h, k_w = tc._khw(k)
+    gview = (lambda n: group.g(n)) if wshape is None else (lambda n: group.g(n).view(wshape))
+    direct = cpad == cout and len(wnames) == 1 and cin_real == cin
+    if direct:
+        gw = gview(wnames[0])
+    else:
+        gw = ctx.zeros(k_h * k_w * cin * cpad).view(k_h, k_w, cin, cpad)
+    c0 = 0
+    for s, shp in zip(srcs, shapes):
+        C = shp[3]
+        wplan = ctx.plan("wgrad", (shp, k, stride, pad, cpad, c0, cin),
+                         lambda shp=shp, c0=c0, C=C: tc.plan_conv_wgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
+        wplan.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
+        cv.run_wgrad(wplan, s, dy, gw)
+        c0 += C
+    if not direct:
+        o = 0
+        for n in wnames:
+            co = ctx.p(n).shape[3]
+            gview(n).add_(gw[:, :, :cin_real, o:o + co])
+            o += co
+    if bnames:
+        gb = ctx.zeros(cpad)
+        ops.channel_sum(dy, gb)
+        o = 0
+        for n in bnames:
+            co = ctx.p(n).shape[0]
+            group.g(n).add_(gb[o:o + co])
+            o += co
+
+
 def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, cout, dy, group, need_input_grad,
                            cin_real, wshape, parents=None, rows=None):
     """dy: bf16 gradient w.r.t. the convolution output, [N,Ho,Wo,cpad] with cpad = round_up(cout, 8).
@@ -388,35 +485,17 @@ def _conv_backward(ctx, tape, srcs, shapes, wnames, bnames, w, k, stride, pad, c
     train = group.trainable and ((group is ctx.G and ctx.train_G) or (group is ctx.D and ctx.train_D))
     cin = sum(s[3] for s in shapes)
     if train:
-        k_h, k_w = tc._khw(k)
-        gview = (lambda n: group.g(n)) if wshape is None else (lambda n: group.g(n).view(wshape))
-        direct = cpad == cout and len(wnames) == 1 and cin_real == cin
-        if direct:
-            gw = gview(wnames[0])
+        ws = ctx.wgrad_stream
+        if ws is not None:
+            ws.wait_stream(torch.cuda.current_stream())        # dy is complete on the main stream
+            ctx._wg_keep.append((dy, srcs))
+            ctx._wg_pending = True
+            if ctx not in tape.joins:
+                tape.joins.append(ctx)
+            with torch.cuda.stream(ws):
+                _weight_grads(ctx, srcs, shapes, wnames, bnames, k, stride, pad, cout, dy, group, cin_real, wshape, cin, cpad)
         else:
-            gw = ctx.zeros(k_h * k_w * cin * cpad).view(k_h, k_w, cin, cpad)
-        c0 = 0
-        for s, shp in zip(srcs, shapes):
-            C = shp[3]
-            wplan = ctx.plan("wgrad", (shp, k, stride, pad, cpad, c0, cin),
-                             lambda shp=shp, c0=c0, C=C: tc.plan_conv_wgrad(shp, k, stride, pad, cpad, cin_slice=(c0, c0 + C, cin)))
-            wplan.flop_scale = (cin_real / float(cin)) * (cout / float(cpad))
-            cv.run_wgrad(wplan, s, dy, gw)
-            c0 += C
-        if not direct:
-            o = 0
-            for n in wnames:
-                co = ctx.p(n).shape[3]
-                gview(n).add_(gw[:, :, :cin_real, o:o + co])
-                o += co
-        if bnames:
-            gb = ctx.zeros(cpad)
-            ops.channel_sum(dy, gb)
-            o = 0
-            for n in bnames:
-                co = ctx.p(n).shape[0]
-                group.g(n).add_(gb[o:o + co])
-                o += co
+            _weight_grads(ctx, srcs, shapes, wnames, bnames, k, stride, pad, cout, dy, group, cin_real, wshape, cin, cpad)
     if not need_input_grad:
         return
     c0 = 0

@@ -61,6 +61,8 @@ class DetectorTranslatorModel(BaseModel):
         self.overlap_g_allreduce = os.environ.get("KP_OVERLAP_G_ALLREDUCE", "1") != "0"
         self._g_pending = False
         self._g_done = []
+        # weight gradients on their own stream beside the data-gradient chain (engine.Context.wgrad_stream)
+        self.overlap_wgrad = os.environ.get("KP_WGRAD_STREAM", "1") != "0"
         # outputs of the last forward pass (names follow the reference's attributes)
         self.final_output = self.crude_output = self.mask = None
         self.current_keypoints = self.future_keypoints = None
@@ -68,6 +70,10 @@ class DetectorTranslatorModel(BaseModel):
         self.loss_D_real = self.loss_D_fake = self.loss_G_recon = self.loss_G_adv = None
 
         self.ctx = E.Context(self.device, n_pts=self.n_points)
+        if self.overlap_wgrad and is_training and self.device.type == "cuda":
+            self.ctx.wgrad_stream = torch.cuda.Stream(device=self.device)
+        if os.environ.get("KP_BRANCH_STREAM", "1") != "0" and self.device.type == "cuda":
+            self.ctx.branch_stream = torch.cuda.Stream(device=self.device)
         networks.build_parameters(self.ctx, self.n_points, with_vgg=True)
         self._init_weights(seed)
         if self.world > 1:
@@ -128,8 +134,10 @@ class DetectorTranslatorModel(BaseModel):
         """reference :160-184.  Returns the heads tensor too (crude+mask before compose)."""
         networks.set_context(self.ctx)
         tm = self.is_training
-        embeddings = networks.image_encoder(im, tm) if for_G_run else \
-            [im] + networks.encoder(networks._prep7(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
+        # image_encoder and pose_encoder are independent until the translator: the shorter one runs on the branch stream
+        with self.ctx.branch():
+            embeddings = networks.image_encoder(im, tm) if for_G_run else \
+                [im] + networks.encoder(networks._prep7(im), tm, _scope="image_encoder/encoder/", _n_blocks=3) + [None]
         self._grad_bucket_marker("pose_encoder/")        # runs (in the backward pass) after BOTH pose_encoder calls are done
         if self.batch_shared_passes:
             # pose_encoder(im) and pose_encoder(future_im) as one pass over [im; future_im] with per-call BN statistics
@@ -138,6 +146,7 @@ class DetectorTranslatorModel(BaseModel):
         else:
             current_gauss_pt, current_pt_map = networks.pose_encoder_with_maps(im, self.n_points, tm, (32, 32))
             future_gauss_pt, future_pt_map = networks.pose_encoder_with_maps(future_im, self.n_points, tm, (32, 32))
+        self.ctx.branch_join()
         joint_embedding = networks.joint_embedding(embeddings[-2], current_pt_map, future_pt_map)
         self._grad_bucket_marker("translator/")          # ... after the translator's last weight gradient
         heads = networks.translator_heads(joint_embedding, tm)
@@ -175,6 +184,28 @@ class DetectorTranslatorModel(BaseModel):
         ctx = self.ctx
         loss = torch.zeros(2, device=self.device)             # [reconstruction, adversarial]
         tape = ctx.tape
+        # The adversarial chain D(fake) and the perceptual chain VGG([gt; pred]) are independent, forward and backward,
+        # and meet only in the gradient of the generated frame: D(fake) runs on the branch stream (issued FIRST, so that in
+        # the backward pass its closures come last and overlap the VGG backward).  It reads the frame through an alias with
+        # its own gradient buffer; the two gradients are added after the branch has joined.
+        pred_D = future_im_pred.view(future_im_pred.shape)
+        if backward:
+            def merge_bwd():
+                g = tape.grad(pred_D)
+                if g is None:
+                    return
+                dx, acc = tape.acquire(future_im_pred, dtype=g.dtype)
+                if acc:
+                    dx.add_(g)
+                else:
+                    dx.copy_(g)
+            tape.record(merge_bwd)
+        with ctx.branch():
+            self._join_D()                      # the discriminator update of the D run must have landed
+            fake_ = networks.img_discr(pred_D, need_input_grad=backward)
+            d_adv = ops.bce_logits(fake_, 1.0, 1.0, loss[1:2], backward)
+            if backward:
+                tape.set_grad(fake_, d_adv)
         if self.batch_shared_passes:
             # VGG on [gt; pred] in one pass like the reference (:274-279); only the generated half carries a gradient
             B = future_im.shape[0]
@@ -208,11 +239,7 @@ class DetectorTranslatorModel(BaseModel):
                 ops.l1_pair(fg, fp, 1.0 / len(feat_pred), loss[0:1], d)
                 if backward:
                     tape.set_grad(fp, d)
-        self._join_D()                      # the discriminator update of the D run must have landed
-        fake_ = networks.img_discr(future_im_pred, need_input_grad=backward)
-        d_adv = ops.bce_logits(fake_, 1.0, 1.0, loss[1:2], backward)
-        if backward:
-            tape.set_grad(fake_, d_adv)
+        ctx.branch_join()
         return loss
 
     def _allreduce(self, buf):
@@ -244,6 +271,7 @@ class DetectorTranslatorModel(BaseModel):
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             self._side.wait_stream(main)
+            ctx.join_wgrad(waiter=self._side)        # the bucket's weight gradients may still run on their own stream
             with torch.cuda.stream(self._side):
                 self._allreduce(ctx.G.grad[lo:hi])
             self._g_pending = True
@@ -260,10 +288,11 @@ class DetectorTranslatorModel(BaseModel):
         loss = self._compute_loss_D(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.train_D = None, False
-        if self.world > 1 and self.overlap_d_update:
-            # Data parallel: the 179 MB all-reduce of the discriminator gradients, Adam(D) and the D weight re-pack run on
+        if self.overlap_d_update and self.device.type == "cuda":
+            # The 179 MB all-reduce of the discriminator gradients (data parallel), Adam(D) and the D weight re-pack run on
             # a side stream while the G run's generator forward (which does not touch img_discr) proceeds; the streams
             # join right before the G run's D(fake) (_join_D).  Inside the captured graph this is a fork/join of nodes.
+            # On one GPU it still pays: the HBM-bound update kernels run beside tensor-bound convolutions.
             main = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
@@ -346,7 +375,12 @@ class DetectorTranslatorModel(BaseModel):
         from .. import _lib
         n0 = _lib.load().kp_launch_count()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        # the main chain is captured from a high-priority stream: where a side stream's kernel (weight gradients, the D
+        # update) and the next kernel of the chain are both ready, the chain gets the SMs first
+        prio = int(os.environ.get("KP_GRAPH_PRIORITY", "-1"))
+        cap = torch.cuda.Stream(device=dev, priority=prio)
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(self._graph, stream=cap):
             lD = self._run_D(self._static[0], self._static[1])
             lG = self._run_G(self._static[2], self._static[3])
         self.graph_launches = int(_lib.load().kp_launch_count() - n0)   # library kernels recorded per replay
