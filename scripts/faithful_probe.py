@@ -65,8 +65,7 @@ def main():
     ctx.tape, ctx.train_G, ctx.train_D = tape, True, False
     fake_dev = fake_ref.to(dev).contiguous()
     loss = model._compute_loss_G(fake_dev, fut.to(dev), backward=True)
-    for fn in reversed(tape.ops):
-        fn()
+    tape.run_closures()
     d_fake = tape.grad(fake_dev)
     torch.cuda.synchronize()
     print("loss_G cuda", loss.tolist(), "oracle", float(lG[1]), float(lG[2]))

@@ -90,8 +90,7 @@ def test_conv_bn_relu_layer_forward_backward(cuda_dev, case):
     grads_x = None
 
     # capture dx before the tape clears: run backward manually
-    for fn in reversed(tape.ops):
-        fn()
+    tape.run_closures()
     grads_x = [tape.grad(sx) for sx in srcs]
 
     # oracle: fp64 autograd on the same rounded operands
@@ -157,8 +156,7 @@ def test_conv_bias_act_layer_forward_backward(cuda_dev, act, cout, out_f32):
         dout = torch.from_numpy(rng.normal(size=(N, H, W, cout)).astype(np.float32)).to(BF)
         ctx.tape.set_grad(y, dout.to(cuda_dev))
         ref.backward(dout.double())
-    for fn in reversed(ctx.tape.ops):
-        fn()
+    ctx.tape.run_closures()
     _close(ctx.G.g("t/conv2d/kernel"), w64.grad, 1e-2, "dW")
     _close(ctx.G.g("t/conv2d/bias"), b64.grad, 1e-2, "dbias")
     _close(ctx.tape.grad(xd), x64.grad, 1.5e-2, "dX")
@@ -220,8 +218,7 @@ def test_conv_layer_at_graph_shapes(cuda_dev, case):
         dy[..., :cout] = dout
     ctx.tape.set_grad(y, dy.to(cuda_dev))
     ref.backward(dout.float())
-    for fn in reversed(ctx.tape.ops):
-        fn()
+    ctx.tape.run_closures()
     _close(ctx.G.g("t/conv2d/kernel"), w32.grad, 1e-2, "dW")
     if use_bias:
         _close(ctx.G.g("t/conv2d/bias"), b32.grad, 1e-2, "dbias")
@@ -244,8 +241,7 @@ def test_gradient_accumulation_two_consumers(cuda_dev):
     d1 = torch.from_numpy(rng.normal(size=tuple(y1.shape)).astype(np.float32)).to(BF)
     d2 = torch.from_numpy(rng.normal(size=tuple(y2.shape)).astype(np.float32)).to(BF)
     ctx.tape.set_grad(y1, d1.to(cuda_dev)); ctx.tape.set_grad(y2, d2.to(cuda_dev))
-    for fn in reversed(ctx.tape.ops):
-        fn()
+    ctx.tape.run_closures()
     x64 = x.double().requires_grad_(True)
     (T.conv2d(x64, w1.double(), None, 1, 0) * d1.double()).sum().add((T.conv2d(x64, w2.double(), None, 2, 0) * d2.double()).sum()).backward()
     _close(ctx.tape.grad(xd), x64.grad, 1.5e-2, "accumulated dX")
@@ -460,8 +456,7 @@ def test_w_unrolled_first_layer_matches_square_conv(cuda_dev, k, cpad, cout, wit
     dout = torch.from_numpy(rng.normal(size=tuple(y.shape)).astype(np.float32)).to(BF)
     ctx.tape.set_grad(y, dout.to(cuda_dev))
     ref.backward(dout.double())
-    for fn in reversed(ctx.tape.ops):
-        fn()
+    ctx.tape.run_closures()
     _close(ctx.G.g("t/conv2d/kernel"), w64.grad, 1e-2, "dW")
     # image gradient through the adjoint of the unrolling (and of the affine preprocessing)
     g = ctx.tape.grad(xp)
@@ -669,8 +664,7 @@ def test_two_layer_chain_forward_backward(cuda_dev, geom):
     dout = torch.from_numpy(rng.normal(size=tuple(h2.shape)).astype(np.float32)).to(BF)
     ctx.tape.set_grad(h2, dout.to(cuda_dev))
     tape = ctx.tape
-    for fn in reversed(tape.ops):
-        fn()
+    tape.run_closures()
     dx = tape.grad(xd)
     # oracle
     x64 = x.double().requires_grad_(True)

@@ -92,13 +92,18 @@ class Tape:
         self.g[k] = buf
         return buf, False
 
-    def backward(self):
+    def run_closures(self):
+        """The recorded closures in reverse order, each on the stream it was recorded on; the gradients stay (tests read
+        them before clearing)."""
         for fn, st in reversed(self.ops):
             if st is None:
                 fn()
             else:
                 with torch.cuda.stream(st):
                     fn()
+
+    def backward(self):
+        self.run_closures()
         for c in self.joins:
             c.join_wgrad()
         self.joins.clear()
@@ -124,8 +129,8 @@ class Context:
         self.train_G = False
         self.debug = None                             # dict: layer scope -> internals (tests / probes only)
         self.trace = None                             # list of dicts, one per stored tensor in call order (tests only)
-        self.zpool = None
-        self.zoff = 0
+        self._zp = {}                 # slot -> zero pool state
+        self._z = None                # the pool of the run being issued
         # Weight gradients on their own stream (set by the model): in the backward pass a layer's weight gradient depends
         # only on (saved input, dy) and nobody needs it before the optimizer, so it runs beside the data-gradient chain
         # (next layer's BN backward = HBM-bound, data gradient = tensor-bound) and fills the tails of those launches.
@@ -141,30 +146,35 @@ class Context:
     # ---- pooled zero-initialised scratch (BN statistics, per-call gradient sums): ONE memset per run ----
     ZPOOL_FLOATS = 4 * 1024 * 1024
 
-    def begin_run(self):
-        """Call at the start of every forward(/backward) run: re-zeroes the scratch pool with a single memset."""
-        if self.zpool is None:
-            self.zpool = torch.zeros(self.ZPOOL_FLOATS, device=self.device, dtype=F32)
-            self.zhigh = 0
+    def begin_run(self, slot=0):
+        """Call at the start of every forward(/backward) run: re-zeroes the scratch pool with a single memset.
+        slot: runs that overlap on different streams (the D run beside the G run) use different pools."""
+        z = self._zp.get(slot)
+        if z is None:
+            z = self._zp[slot] = {"pool": torch.zeros(self.ZPOOL_FLOATS, device=self.device, dtype=F32), "off": 0, "high": 0,
+                                  "captured": None}
         else:
             # Re-zero up to the HIGH-WATER mark of all runs so far, not just the previous run's extent: inside a captured
             # CUDA graph this memset has a fixed length, and an eager run in between (test_step) may have used more.
-            self.zhigh = max(self.zhigh, self.zoff, 1)
+            z["high"] = max(z["high"], z["off"], 1)
             if torch.cuda.is_current_stream_capturing():
-                self.zcaptured = self.zhigh
-            elif getattr(self, "zcaptured", None) is not None and self.zhigh > self.zcaptured:
+                z["captured"] = z["high"]
+            elif z["captured"] is not None and z["high"] > z["captured"]:
                 # scratch beyond what the captured memset clears was dirtied: clear it now, eagerly
-                self.zpool[self.zcaptured:self.zhigh].zero_()
-            self.zpool[:self.zhigh].zero_()
-        self.zoff = 0
+                z["pool"][z["captured"]:z["high"]].zero_()
+            z["pool"][:z["high"]].zero_()
+        z["off"] = 0
+        self._z = z
 
     def zeros(self, n):
-        """n zeroed floats valid until the next begin_run() (falls back to torch.zeros when the pool is exhausted)."""
+        """n zeroed floats valid until the next begin_run() of the same slot (falls back to torch.zeros when the pool is
+        exhausted)."""
         n4 = (n + 3) // 4 * 4
-        if self.zpool is None or self.zoff + n4 > self.zpool.numel():
+        z = self._z
+        if z is None or z["off"] + n4 > z["pool"].numel():
             return torch.zeros(n, device=self.device, dtype=F32)
-        out = self.zpool[self.zoff:self.zoff + n]
-        self.zoff += n4
+        out = z["pool"][z["off"]:z["off"] + n]
+        z["off"] += n4
         return out
 
     def branch(self):

@@ -51,7 +51,8 @@ class DetectorTranslatorModel(BaseModel):
         self._graph = None
         self._lr_dev = None
         self._static = None
-        self._side = None                  # side stream for the overlapped discriminator update (data parallel only)
+        self._side = None                  # second stream: the D run beside the G run's forward / perceptual chain
+        self._side_branch = None
         self._d_pending = False
         self.overlap_d_update = os.environ.get("KP_OVERLAP_D_UPDATE", "1") != "0"
         # the two pose_encoder calls and VGG(gt) / VGG(pred) run as single batched passes (KP_BATCH_SHARED=0: separate calls)
@@ -73,7 +74,7 @@ class DetectorTranslatorModel(BaseModel):
         if self.overlap_wgrad and is_training and self.device.type == "cuda":
             self.ctx.wgrad_stream = torch.cuda.Stream(device=self.device)
         if os.environ.get("KP_BRANCH_STREAM", "1") != "0" and self.device.type == "cuda":
-            self.ctx.branch_stream = torch.cuda.Stream(device=self.device)
+            self.ctx.branch_stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("KP_BRANCH_PRIORITY", "0")))
         networks.build_parameters(self.ctx, self.n_points, with_vgg=True)
         self._init_weights(seed)
         if self.world > 1:
@@ -279,8 +280,31 @@ class DetectorTranslatorModel(BaseModel):
 
     # ---- the two runs of one train step ----
     def _run_D(self, im, future_im):
+        if self.overlap_d_update and self.device.type == "cuda":
+            # The D run (generator forward without gradient on ITS batch, img_discr forward/backward, gradient all-reduce,
+            # Adam(D), weight re-pack) shares nothing with the G run's generator forward and perceptual chain - they read
+            # the same generator weights and meet only at the G run's D(fake), which needs the updated discriminator
+            # (_join_D).  So the whole run goes to a second stream and the two chains fill each other's launch tails and
+            # pair HBM-bound with tensor-bound kernels.  Inside the captured graph this is a fork/join of nodes.
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("KP_DCHAIN_PRIORITY", "-1")))
+            if self._side_branch is None:
+                self._side_branch = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            keep = self.ctx.branch_stream
+            if keep is not None:
+                self.ctx.branch_stream = self._side_branch
+            with torch.cuda.stream(self._side):
+                loss = self._run_D_body(im, future_im)
+            self.ctx.branch_stream = keep
+            self._d_pending = True
+            return loss
+        return self._run_D_body(im, future_im)
+
+    def _run_D_body(self, im, future_im):
         ctx = self.ctx
-        ctx.begin_run()
+        ctx.begin_run(0)
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = None, False, False, False
         fake = self._define_forward_pass(im, future_im, for_G_run=False)
         ctx.tape, ctx.train_D = E.Tape(), True
@@ -288,20 +312,7 @@ class DetectorTranslatorModel(BaseModel):
         loss = self._compute_loss_D(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.train_D = None, False
-        if self.overlap_d_update and self.device.type == "cuda":
-            # The 179 MB all-reduce of the discriminator gradients (data parallel), Adam(D) and the D weight re-pack run on
-            # a side stream while the G run's generator forward (which does not touch img_discr) proceeds; the streams
-            # join right before the G run's D(fake) (_join_D).  Inside the captured graph this is a fork/join of nodes.
-            # On one GPU it still pays: the HBM-bound update kernels run beside tensor-bound convolutions.
-            main = torch.cuda.current_stream()
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                self._finish_D()
-            self._d_pending = True
-        else:
-            self._finish_D()
+        self._finish_D()
         return loss
 
     def _finish_D(self):
@@ -319,7 +330,7 @@ class DetectorTranslatorModel(BaseModel):
 
     def _run_G(self, im, future_im):
         ctx = self.ctx
-        ctx.begin_run()
+        ctx.begin_run(1)                   # its own scratch pool: the D run may still be running on the other stream
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = E.Tape(), True, True, False
         ctx.G.grad.zero_()
         self._g_done = []
