@@ -60,8 +60,8 @@ class DetectorTranslatorModel(BaseModel):
         # data parallel: all-reduce the generator gradients in buckets (translator / pose_encoder / image_encoder, the
         # order in which the backward pass completes them) on the side stream, under the rest of the backward pass
         self.overlap_g_allreduce = os.environ.get("KP_OVERLAP_G_ALLREDUCE", "1") != "0"
-        self._g_pending = False
-        self._g_done = []
+        self._comm = None                  # communication stream of the bucketed gradient all-reduces
+        self._done = {"G": [], "D": []}      # gradient slices already handed to an all-reduce in this backward pass
         # weight gradients on their own stream beside the data-gradient chain (engine.Context.wgrad_stream)
         self.overlap_wgrad = os.environ.get("KP_WGRAD_STREAM", "1") != "0"
         # outputs of the last forward pass (names follow the reference's attributes)
@@ -173,7 +173,7 @@ class DetectorTranslatorModel(BaseModel):
         ctx = self.ctx
         B = future_im.shape[0]
         x = torch.cat([future_im, future_im_pred.detach()], dim=0)
-        logits = networks.img_discr(x)                       # [2B,6,6,1]: real half then fake half
+        logits = networks.img_discr(x, marker=self._d_marker if backward else None)    # [2B,6,6,1]: real half then fake half
         loss = torch.zeros(2, device=self.device)
         d_real = ops.bce_logits(logits[:B], 1.0, 1.0, loss[0:1], backward)
         d_fake = ops.bce_logits(logits[B:], 0.0, 1.0, loss[1:2], backward)
@@ -257,26 +257,62 @@ class DetectorTranslatorModel(BaseModel):
         assert inside == len(offs), "variables of %r are not contiguous in the flat buffer" % prefix
         return lo, hi
 
+    def _comm_stream(self):
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=self.device, priority=-1)
+        return self._comm
+
+    def _allreduce_marker(self, which, lo, hi):
+        """Tape entry recorded BEFORE the forward of the layers that own the flat gradient slice [lo, hi): in the backward pass
+        it runs right after their last weight gradient has been issued and starts the all-reduce of that bucket on the
+        communication stream while the backward pass of the layers further upstream goes on (data parallel only; the rest
+        and the join are in _finish_allreduce, before Adam)."""
+        ctx = self.ctx
+        grad = ctx.G.grad if which == "G" else ctx.D.grad
+        self._done[which].append((lo, hi))
+
+        def fire():
+            c = self._comm_stream()
+            c.wait_stream(torch.cuda.current_stream())
+            ctx.join_wgrad(waiter=c)                 # the bucket's weight gradients may still run on their own stream
+            with torch.cuda.stream(c):
+                self._allreduce(grad[lo:hi])
+        ctx.tape.record(fire)
+
     def _grad_bucket_marker(self, prefix):
-        """Tape entry recorded BEFORE a network's forward: in the backward pass it runs right after that network's last
-        weight gradient, and starts the all-reduce of its gradient bucket on the side stream while the backward pass of the
-        networks further upstream goes on (data parallel only; joined in _run_G before Adam)."""
         ctx = self.ctx
         if ctx.tape is None or self.world <= 1 or not self.overlap_g_allreduce or not ctx.train_G:
             return
         lo, hi = self._bucket_range(prefix)
-        self._g_done.append((lo, hi))
+        self._allreduce_marker("G", lo, hi)
 
-        def fire():
-            main = torch.cuda.current_stream()
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-            self._side.wait_stream(main)
-            ctx.join_wgrad(waiter=self._side)        # the bucket's weight gradients may still run on their own stream
-            with torch.cuda.stream(self._side):
-                self._allreduce(ctx.G.grad[lo:hi])
-            self._g_pending = True
-        ctx.tape.record(fire)
+    def _d_marker(self, scope):
+        """img_discr calls this before each layer.  Buckets in the order the backward pass completes them: [conv_5, D_logit]
+        (3/4 of the 179 MB) right after the first two layers of the backward pass, then [conv_3, conv_4]; conv_0..2 are
+        the rest."""
+        ctx = self.ctx
+        if ctx.tape is None or self.world <= 1 or not self.overlap_g_allreduce or not ctx.train_D:
+            return
+        D = ctx.D
+        off = lambda pre: min(o for name, _, o in D.specs if name.startswith(pre))
+        if scope == "img_discr/conv_5/":
+            self._allreduce_marker("D", off(scope), D.total)
+        elif scope == "img_discr/conv_3/":
+            self._allreduce_marker("D", off(scope), off("img_discr/conv_5/"))
+
+    def _finish_allreduce(self, which):
+        """After the backward pass: all-reduce what the markers have not sent, then wait for the communication stream."""
+        if self.world <= 1:
+            return
+        grad = self.ctx.G.grad if which == "G" else self.ctx.D.grad
+        done, self._done[which] = sorted(self._done[which]), []
+        pos = 0
+        for lo, hi in done + [(grad.numel(), grad.numel())]:
+            if lo > pos:
+                self._allreduce(grad[pos:lo])
+            pos = max(pos, hi)
+        if done:
+            torch.cuda.current_stream().wait_stream(self._comm_stream())
 
     # ---- the two runs of one train step ----
     def _run_D(self, im, future_im):
@@ -309,6 +345,7 @@ class DetectorTranslatorModel(BaseModel):
         fake = self._define_forward_pass(im, future_im, for_G_run=False)
         ctx.tape, ctx.train_D = E.Tape(), True
         ctx.D.grad.zero_()
+        self._done["D"] = []
         loss = self._compute_loss_D(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.train_D = None, False
@@ -317,7 +354,7 @@ class DetectorTranslatorModel(BaseModel):
 
     def _finish_D(self):
         ctx = self.ctx
-        self._allreduce(ctx.D.grad)
+        self._finish_allreduce("D")
         self.t_D += 1
         ops.adam_tf(ctx.D.data, ctx.D.grad, ctx.D.m, ctx.D.v, self._current_lr(), self.t_D, grad_scale=1.0 / self.world,
                     lr_t_dev=self._lr_dev[0:1] if self._lr_dev is not None else None)
@@ -333,26 +370,13 @@ class DetectorTranslatorModel(BaseModel):
         ctx.begin_run(1)                   # its own scratch pool: the D run may still be running on the other stream
         ctx.tape, ctx.update_moving, ctx.train_G, ctx.train_D = E.Tape(), True, True, False
         ctx.G.grad.zero_()
-        self._g_done = []
+        self._done["G"] = []
         fake = self._define_forward_pass(im, future_im, for_G_run=True)
         loss = self._compute_loss_G(fake, future_im, backward=True)
         ctx.tape.backward()
         ctx.tape, ctx.update_moving, ctx.train_G = None, False, False
         self._join_D()
-        if self.world > 1:
-            # whatever the bucket markers have not sent yet (image_encoder: complete only now), then join the side stream
-            rest, pos = [], 0
-            for lo, hi in sorted(self._g_done):
-                if lo > pos:
-                    rest.append((pos, lo))
-                pos = max(pos, hi)
-            if pos < ctx.G.grad.numel():
-                rest.append((pos, ctx.G.grad.numel()))
-            for lo, hi in rest:
-                self._allreduce(ctx.G.grad[lo:hi])
-            if self._g_pending:
-                torch.cuda.current_stream().wait_stream(self._side)
-                self._g_pending = False
+        self._finish_allreduce("G")
         self.t_G += 1
         ops.adam_tf(ctx.G.data, ctx.G.grad, ctx.G.m, ctx.G.v, self._current_lr(), self.t_G, grad_scale=1.0 / self.world,
                     lr_t_dev=self._lr_dev[1:2] if self._lr_dev is not None else None)

@@ -319,14 +319,18 @@ def _prep_with_grad(ctx, x, prep, unroll=None):
     return xp
 
 
-def img_discr(x, need_input_grad=False):
-    """reference networks/__init__.py:141-151: image [B,128,128,3] -> logit [B,6,6,1] float32."""
+def img_discr(x, need_input_grad=False, marker=None):
+    """reference networks/__init__.py:141-151: image [B,128,128,3] -> logit [B,6,6,1] float32.
+    marker(scope): called before each layer is recorded; the data-parallel train step hangs the all-reduce of a gradient
+    bucket on it (a tape entry recorded there runs, in the backward pass, right after that layer's gradients)."""
     ctx = get_context()
     h = _prep_with_grad(ctx, x, ops.IDENT_PREP) if need_input_grad else ops.image_prep(x)
     h = E.conv_layer(ctx, [h], "img_discr/conv_0/conv2d/kernel", "img_discr/conv_0/conv2d/bias", 4, 2, 1, act=tc.ACT_LEAKY,
                      alpha=0.01, need_input_grad=need_input_grad)
     for i in range(1, 6):
         sc = "img_discr/conv_%d" % i
+        if marker is not None:
+            marker(sc + "/")
         h = E.conv_layer(ctx, [h], sc + "/conv2d/kernel", sc + "/conv2d/bias", 4, 2, 1, act=tc.ACT_LEAKY, alpha=0.01)
     return E.conv_layer(ctx, [h], "img_discr/D_logit/conv2d/kernel", None, 3, 1, 1, out_f32=True)
 
