@@ -755,6 +755,14 @@ def run_ours(args):
         step_tflops = TRAIN_GFLOP_PER_EXAMPLE * B / (ms_per_step * 1e-3) / 1e3
         peak = peaks["bf16_tflops_sustained"]
         achieved = (kern or {}).get("conv_tflops") or step_tflops
+        # DRAM bytes of all conv launches of one step, from the committed ncu launch list of the eager step
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "train_traffic.json")) as fh:
+                tj = json.load(fh)
+            traffic, traffic_src = tj["conv_dram_bytes_per_step"], tj["source"] + " - sum over the conv launches of one step"
+        except (OSError, KeyError, ValueError):
+            pass
         cpu = None
         if world == 1 and not args.no_cpu:
             try:
@@ -771,7 +779,9 @@ def run_ours(args):
             "config": train_config(world, B),
             "run": {"examples_per_s": world * B / (ms_per_step * 1e-3), "cuda_graph": not args.no_graph, "losses_last_step": losses},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peaks["source"] + " (sustained: kernels timed inside a long step)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_step": sum(t[2] for t in tags) if tags else None,
+                         "peak_source": peaks["source"] + " (sustained: kernels timed inside a long step)",
                          "kernel": "kp::halo2_kernel / kp::tapconv_kernel / kp::wgrad_kernel: algorithmic FLOPs of all conv launches of "
                                    "one step / their summed durations inside the step (CUPTI activity records of replays of the "
                                    "captured step with the side streams off - see kernels.mode -, zipped with the per-launch tags "
