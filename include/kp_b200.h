@@ -259,7 +259,7 @@ int kp_maxpool2x2_bwd(const void* dy, const void* x, int relu_mask, int N, int H
  * of models/final_model.py:98-99).  heads f32 [P,4] = (crude, sigmoid(mask)) from the fused head conv.  */
 int kp_mask_compose_fwd(const float* heads, const float* im, long long P, int clip, float* final_out, float* crude_out,
                         float* mask_out, void* stream);
-/* d_final f32 [P,3] -> gradient w.r.t. the head pre-activations, bf16 [P,8]. */
+/* d_final f32 [P,3] -> gradient w.r.t. the head pre-activations, bf16 [P,16] (channels 4..15 zero). */
 int kp_mask_compose_bwd(const float* d_final, const float* heads, const float* im, long long P, void* d_heads, void* stream);
 /* tf.concat on channels with cast to bf16 and zero padding to Ctot (joint embedding,
  * models/detector_translator_model.py:170), and its adjoint.  src/C/is_f32 are HOST arrays.          */

@@ -630,7 +630,9 @@ __global__ void compose_fwd_kernel(const float* __restrict__ heads, const float*
         if (mask_out) mask_out[p] = m;
     }
 }
-// d_final f32 [P,3] -> gradient w.r.t. the head PRE-activations, bf16 [P,8] (crude 3, mask logit 1, 4 zeros)
+// d_final f32 [P,3] -> gradient w.r.t. the head PRE-activations, bf16 [P,16] (crude 3, mask logit 1, 12 zeros): 16 channels
+// are one channel slot of the halo kernels (conv_halo2.cu data gradient, conv_wgrad2.cu); with 8 the heads' backward ran on
+// the per-tap kernels at 0.8-1.1 TB/s
 __global__ void compose_bwd_kernel(const float* __restrict__ d_final, const float* __restrict__ heads,
                                    const float* __restrict__ im, long long P, __nv_bfloat16* __restrict__ d_heads) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -646,7 +648,9 @@ __global__ void compose_bwd_kernel(const float* __restrict__ d_final, const floa
             dm = fmaf(g, im[3 * p + c] - cr[c], dm);
         }
         f[3] = dm * m * (1.f - m);
-        *reinterpret_cast<uint4*>(d_heads + 8 * p) = bf8_pack(f);
+        uint4* o = reinterpret_cast<uint4*>(d_heads + 16 * p);
+        o[0] = bf8_pack(f);
+        o[1] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 

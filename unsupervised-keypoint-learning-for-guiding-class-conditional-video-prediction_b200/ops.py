@@ -169,7 +169,7 @@ def compose_fwd(heads, im, clip=False, want_parts=False):
 
 def compose_bwd(d_final, heads, im):
     P = im.numel() // 3
-    out = torch.empty(tuple(im.shape[:-1]) + (8,), device=im.device, dtype=BF16)
+    out = torch.empty(tuple(im.shape[:-1]) + (16,), device=im.device, dtype=BF16)
     _lib.call("kp_mask_compose_bwd", _p(d_final), _p(heads), _p(im), P, _p(out), _st())
     return out
 
