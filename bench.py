@@ -597,6 +597,137 @@ def bench_k1(args, world, rank, dev, lib):
                          "kernel": "kp::k1_fwd_fast<5,8>", "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME * B}}
 
 
+INPUT_BYTES_PER_FRAME = 128 * 128 * 3 * (1 + 4)     # bytes gathered (one per output byte) + float32 output written
+
+
+def _synthetic_jpeg_dataset(root, videos=8, frames=24, size=(320, 240), seed=0):
+    """<root>/frames/%04d/%06d.jpg + train_set.txt, the layout data/image_pair_dataloader.py reads."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    w, h = size
+    yy, xx = np.mgrid[0:h, 0:w]
+    names = []
+    for v in range(videos):
+        d = os.path.join(root, "frames", "%04d" % (v + 1))
+        os.makedirs(d, exist_ok=True)
+        names.append("frames/%04d %d" % (v + 1, v % 3))
+        a, ph = rng.uniform(0.02, 0.09, (3, 2)), rng.uniform(0, 6.28, 3)
+        for t in range(frames):
+            img = np.stack([127 + 110 * np.sin(a[c, 0] * xx + ph[c] + 0.1 * t) * np.cos(a[c, 1] * yy - ph[c]) for c in range(3)], -1)
+            img = np.clip(img + rng.normal(0, 10, img.shape), 0, 255).astype(np.uint8)
+            Image.fromarray(img).save(os.path.join(d, "%06d.jpg" % (t + 1)), quality=85)
+    with open(os.path.join(root, "train_set.txt"), "w") as fh:
+        fh.write("\n".join(names))
+
+
+def _pillow_pair(root, names, rnd):
+    """cpu_baseline leg only: one training pair through the reference's Pillow call sequence (data/image_pair_dataloader.py:
+    72-165, utils/data.py:8-35; resize resample NEAREST = the pinned Pillow 6.2.0 default), on the installed Pillow."""
+    import numpy as np
+    from PIL import Image, ImageEnhance, ImageFilter
+    folder = os.path.join(root, names[rnd.randrange(len(names))].split()[0])
+    n = len(os.listdir(folder))
+    step, i0 = rnd.randint(8, 11), rnd.randint(0, n - 1)
+    ims = [Image.open(os.path.join(folder, "%06d.jpg" % (i + 1))) for i in (i0, (i0 + step) % n)]
+    w, h = ims[0].size
+    ang = rnd.randrange(-10, 11)
+    ims = [im.rotate(ang) for im in ims]
+    ratio = min(w, h) / 128.0
+    ims = [im.resize([int(w / ratio), int(h / ratio)], Image.NEAREST) for im in ims]
+    c = rnd.randint(0, int(max(w, h) / ratio - 128))
+    box = (c, 0, c + 128, 128) if w > h else (0, c, 128, c + 128)
+    ims = [im.crop(box) for im in ims]
+    if rnd.randint(0, 1):
+        ims = [im.transpose(Image.FLIP_LEFT_RIGHT) for im in ims]
+    r = rnd.randint(0, 9)
+    F = [ImageFilter.DETAIL, ImageFilter.EDGE_ENHANCE, ImageFilter.SMOOTH, ImageFilter.SMOOTH_MORE,
+         ImageFilter.EDGE_ENHANCE_MORE, ImageFilter.BLUR]
+    if r < 6:
+        ims = [im.filter(F[r]) for im in ims]
+    else:
+        E, (lo, hi) = [(ImageEnhance.Sharpness, (0, 50)), (ImageEnhance.Brightness, (7, 20)), (ImageEnhance.Color, (0, 50)),
+                       (ImageEnhance.Contrast, (7, 30))][r - 6]
+        v = rnd.randint(lo, hi) * 0.1
+        ims = [E(im).enhance(v) for im in ims]
+    return [(np.asarray(im) / 255.0).astype(np.float32) * 2.0 - 1.0 for im in ims]
+
+
+def bench_input(args, dev, lib, peaks):
+    """Input pipeline: kp_augment_frames on frames resident in HBM (roofline: HBM), the loader end to
+    end from JPEG files (PIL decode on host threads -> pinned staging -> H2D -> one launch per batch), and the reference's
+    Pillow chain on one host thread beside it."""
+    import random
+    import tempfile
+    import numpy as np
+    import torch
+    from kp_b200 import augment as A
+    from kp_b200 import data
+    n, w, h = args.input_frames, 320, 240                       # 2048 x 230 400 B = 472 MB of decoded frames >> 126 MB L2
+    gen = torch.Generator(device=dev).manual_seed(5)
+    src = torch.randint(0, 256, (n * w * h * 3,), device=dev, dtype=torch.uint8, generator=gen)
+    rnd = random.Random(5)
+    table = A.PlanTable(n)
+    for i in range(n):
+        fid = rnd.randint(0, 9)
+        fac = {6: rnd.randint(0, 50), 7: rnd.randint(7, 20), 8: rnd.randint(0, 50), 9: rnd.randint(7, 30)}.get(fid, 0) * 0.1
+        table.set(i, i * w * h * 3, w, h, 170, 128, rnd.randint(0, 42), 0, rnd.randrange(-10, 11), rnd.randint(0, 1), fid, fac)
+    plans = table.host.to(dev)
+    out = torch.empty((n, 128, 128, 3), device=dev)
+    for _ in range(3):
+        A.augment_frames(src, plans, n, out=out)
+    steps = 20
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lib.kp_launch_count()
+    ev0.record()
+    for _ in range(steps):
+        A.augment_frames(src, plans, n, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    launches = int(lib.kp_launch_count() - n0)
+    del src, out
+    achieved = INPUT_BYTES_PER_FRAME * n / (ms * 1e-3) / 1e9
+    sub = {"workload": "input pipeline of the stage-1 loaders (data/image_pair_dataloader.py:72-165): rotate + resize + crop + flip "
+                       "+ random filter + normalise of %d decoded 320x240 frames per launch, random plans as the reference draws them" % n,
+           "frames_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "gpu_launches": launches, "dtype": "u8",
+           "l2": "decoded frames %d MB + output %d MB per launch >> 126 MB L2" % (n * w * h * 3 >> 20, n * 196608 >> 20),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                        "traffic": None, "peak_source": peaks["source"], "kernel": "kp::augment_kernel",
+                        "algorithmic_bytes_per_launch": INPUT_BYTES_PER_FRAME * n}}
+    with tempfile.TemporaryDirectory() as root:
+        _synthetic_jpeg_dataset(root)
+        np.random.seed(0); random.seed(0)
+        ld = data.ImagePairDataLoader(root, "train", random_order=True, randomness=True)
+        ds = ld.get_dataset(batch_size=32, repeat=True, num_preprocess_threads=_host_threads(), prefetch=True, device=dev)
+        t0, k, acc = None, 0, torch.zeros((), device=dev)
+        for batch in ds:
+            acc += batch["image"][0, 0, 0, 0] + batch["future_image"][0, 0, 0, 0]    # consume on the current stream
+            k += 1
+            if k == 3:
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+            if k == 3 + args.input_batches:
+                break
+        float(acc)      # D2H of a value that depends on every batch
+        sec = time.perf_counter() - t0
+        jpeg = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(root) for f in fs if f.endswith(".jpg"))
+        sub["e2e"] = {"value": 64 * args.input_batches / sec, "unit": "frames/s", "h2d_bytes_per_step": 64 * (w * h * 3 + A.PLAN_BYTES),
+                      "d2h_bytes_per_step": 4, "steps": args.input_batches,
+                      "note": "ImagePairDataLoader.get_dataset(32): JPEG files (%d KB each) -> PIL decode on %d host threads -> pinned "
+                              "staging -> H2D -> one kp_augment_frames launch per batch of 64 frames; bound by the host JPEG decode"
+                              % (jpeg // (8 * 24) >> 10, _host_threads())}
+        names = open(os.path.join(root, "train_set.txt")).read().splitlines()
+        rnd = random.Random(0)
+        t0, pairs = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 3.0:
+            _pillow_pair(root, names, rnd)
+            pairs += 1
+        sub["cpu_baseline"] = {"value": 2 * pairs / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": "%d pairs in 3 s through the reference's Pillow call sequence (decode included) on one host "
+                                         "thread, as its generator runs (tf.data parallelises only map_fn)" % pairs}
+    return sub
+
+
 def run_ours(args):
     import torch
     import __graft_entry__ as g
@@ -742,6 +873,11 @@ def run_ours(args):
         torch.cuda.empty_cache()
         if not args.no_k1:
             subs["k1"] = bench_k1(args, world, rank, dev, lib)
+        try:
+            subs["input"] = bench_input(args, dev, lib, peaks)
+        except Exception as e:
+            subs["input"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
         for kind, st in (("fwd8", 20), ("pseudo", 5), ("render", 5)):
             try:
                 subs[kind] = measure_inference(kind, args, world, rank, dev, lib, peaks, st, 3)
@@ -823,6 +959,8 @@ def main():
     ap.add_argument("--pseudo-frames", type=int, default=4096, help="pseudo: frames per GPU per step")
     ap.add_argument("--render-videos", type=int, default=64, help="render: videos per GPU per step (32 frames each)")
     ap.add_argument("--fwd-pairs", type=int, default=8, help="fwd8: frame pairs per call")
+    ap.add_argument("--input-frames", type=int, default=2048, help="input: decoded frames per launch")
+    ap.add_argument("--input-batches", type=int, default=20, help="input: loader batches (32 pairs) timed end to end")
     ap.add_argument("--cpu-batch", type=int, default=32, help="cpu_baseline of the CUDA arm: oracle train step at this batch")
     ap.add_argument("--cpu-budget", type=int, default=100, help="--impl reference: seconds of timed CPU steps")
     ap.add_argument("--no-graph", action="store_true")

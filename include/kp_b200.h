@@ -290,6 +290,43 @@ int kp_conv1x1_f32(const void* x, const float* w, const float* bias, long long P
 /* out[c] += sum over pixels of g bf16 [P,C] (bias gradients). */
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Input pipeline: the per-frame Pillow chain of the reference's loaders on the device
+ * ------------------------------------------------------------------------------------------- */
+#define KP_AUG_SIZE 128 /* IMAGE_SIZE of data/image_pair_dataloader.py:13, data/keypoint_dataloader.py:13 */
+
+/* What happens to ONE decoded frame (tightly packed HWC uint8 RGB inside the caller's source buffer).  Filled on the host
+ * by kp_augment_plan_host / kp_augment_plan_zero_host, copied to the device by the caller as an array.            */
+typedef struct kp_frame_plan {
+    long long src_offset;      /* byte offset of the frame in the source buffer */
+    int src_w, src_h;
+    int rotate;                /* 1: Image.rotate's nearest-neighbour inverse affine map, 16.16 fixed point */
+    int a[6];                  /* its coefficients (Geometry.c affine_fixed: a0 a1 a2 / a3 a4 a5, centres folded in) */
+    int filter_id;             /* -1 none; 0..5 DETAIL, EDGE_ENHANCE, SMOOTH, SMOOTH_MORE, EDGE_ENHANCE_MORE, BLUR;
+                                  6..9 ImageEnhance Sharpness, Brightness, Color, Contrast (utils/data.py:11-33) */
+    int zero;                  /* 1: an all-zero frame (data/keypoint_dataloader.py:77-80), nothing is read */
+    float factor;              /* enhancement factor of filter_id 6..9 (r_val * 0.1) */
+    short xtab[KP_AUG_SIZE];   /* column / row of the (rotated) source frame behind each output column / row after */
+    short ytab[KP_AUG_SIZE];   /* resize, crop and flip; -1 = outside (stays 0) */
+} kp_frame_plan;
+
+/* HOST function (no CUDA call): the plan of
+ *   image.rotate(angle_deg).resize([resize_w, resize_h]).crop((crop_left, crop_top, crop_left + 128, crop_top + 128))
+ *        [.transpose(FLIP_LEFT_RIGHT)] -> apply_random_filter's branch filter_id with factor
+ *   replaces: data/image_pair_dataloader.py:95-159 (angle_deg 0 and filter_id -1 give the randomness=False branch and
+ *             data/keypoint_dataloader.py:71 `im.resize(...).crop(crop_size)` with utils/data.py:38-59 center_crop).
+ * Pillow 6.2.0 semantics (the reference's pin): rotate and resize resample NEAREST, the crop box goes through
+ * int(round()) (half to even), pixels outside the rotated / resized frame are 0.                                     */
+int kp_augment_plan_host(kp_frame_plan* plan, long long src_offset, int src_w, int src_h, int resize_w, int resize_h,
+                         double crop_left, double crop_top, int angle_deg, int flip, int filter_id, double factor);
+/* HOST function: the plan of one zero frame of the keypoint loader's padding (data/keypoint_dataloader.py:77-80). */
+int kp_augment_plan_zero_host(kp_frame_plan* plan);
+
+/* src: device buffer of decoded frames; plans: DEVICE array [n_frames]; out f32 [n_frames,128,128,3] =
+ * float32(pixel / 255.0) * 2 - 1 (`image / 255.0` of data/image_pair_dataloader.py:162-165 followed by map_fn :63-69).
+ * One launch, byte-exact against Pillow; 49 152 B gathered + 196 608 B written per frame (HBM-bound).               */
+int kp_augment_frames(const unsigned char* src, const kp_frame_plan* plans, int n_frames, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
