@@ -653,6 +653,39 @@ def _pillow_pair(root, names, rnd):
     return [(np.asarray(im) / 255.0).astype(np.float32) * 2.0 - 1.0 for im in ims]
 
 
+def _train_from_files(args, dev, root):
+    """The whole chain a user of train.py runs: JPEG files -> ImagePairDataLoader -> DetectorTranslatorModel.train_step (captured
+    graph), losses read back every step."""
+    import random
+    import numpy as np
+    import torch
+    from kp_b200 import data, models
+    B = args.batch
+    cfg = json.loads(json.dumps(CONFIG))
+    cfg["training"]["batch_size"] = B
+    np.random.seed(1); random.seed(1)
+    ld = data.ImagePairDataLoader(root, "train", random_order=True, randomness=True)
+    ds = ld.get_dataset(batch_size=B, repeat=True, shuffle=True, num_preprocess_threads=_host_threads(), prefetch=True, device=dev)
+    it = iter(ds)
+    model = models.DetectorTranslatorModel(cfg, is_training=True, device=dev, seed=0)
+    model.build(lambda: next(it))
+    model.enable_cuda_graph(B)
+    for _ in range(3):
+        model.train_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.input_train_steps):
+        model.train_step(should_write_log=True)       # reads the losses back
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    ds.close()
+    model._graph = None
+    return {"value": 4 * B * args.input_train_steps / sec, "unit": "frames/s", "ms_per_step": sec / args.input_train_steps * 1e3,
+            "steps": args.input_train_steps,
+            "note": "train_step at batch %d fed by ImagePairDataLoader.get_dataset (JPEG decode in worker processes, augmentation "
+                    "kernel, shuffle buffer) - two batches per step, losses D2H every step" % B}
+
+
 def bench_input(args, dev, lib, peaks):
     """Input pipeline: kp_augment_frames on frames resident in HBM (roofline: HBM), the loader end to
     end from JPEG files (PIL decode on host threads -> pinned staging -> H2D -> one launch per batch), and the reference's
@@ -686,6 +719,18 @@ def bench_input(args, dev, lib, peaks):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / steps
     launches = int(lib.kp_launch_count() - n0)
+    # the keypoint loader's frames (data/keypoint_dataloader.py:71): resize + centre crop only
+    for i in range(n):
+        table.set(i, i * w * h * 3, w, h, 170, 128, 21, 0)
+    plans.copy_(table.host)
+    for _ in range(3):
+        A.augment_frames(src, plans, n, out=out)
+    ev0.record()
+    for _ in range(steps):
+        A.augment_frames(src, plans, n, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_plain = ev0.elapsed_time(ev1) / steps
     del src, out
     achieved = INPUT_BYTES_PER_FRAME * n / (ms * 1e-3) / 1e9
     sub = {"workload": "input pipeline of the stage-1 loaders (data/image_pair_dataloader.py:72-165): rotate + resize + crop + flip "
@@ -694,7 +739,10 @@ def bench_input(args, dev, lib, peaks):
            "l2": "decoded frames %d MB + output %d MB per launch >> 126 MB L2" % (n * w * h * 3 >> 20, n * 196608 >> 20),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                         "traffic": None, "peak_source": peaks["source"], "kernel": "kp::augment_kernel",
-                        "algorithmic_bytes_per_launch": INPUT_BYTES_PER_FRAME * n}}
+                        "algorithmic_bytes_per_launch": INPUT_BYTES_PER_FRAME * n},
+           "resize_crop_only": {"note": "the keypoint loader's plan (no rotation, no filter), same frames", "ms_per_step": ms_plain,
+                                "frames_per_s": n / (ms_plain * 1e-3), "gbs": INPUT_BYTES_PER_FRAME * n / (ms_plain * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": INPUT_BYTES_PER_FRAME * n / (ms_plain * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     with tempfile.TemporaryDirectory() as root:
         _synthetic_jpeg_dataset(root)
         np.random.seed(0); random.seed(0)
@@ -704,18 +752,21 @@ def bench_input(args, dev, lib, peaks):
         for batch in ds:
             acc += batch["image"][0, 0, 0, 0] + batch["future_image"][0, 0, 0, 0]    # consume on the current stream
             k += 1
-            if k == 3:
+            if k == 5:
                 torch.cuda.synchronize(); t0 = time.perf_counter()
-            if k == 3 + args.input_batches:
+            if k == 5 + args.input_batches:
                 break
         float(acc)      # D2H of a value that depends on every batch
         sec = time.perf_counter() - t0
+        ds.close()
         jpeg = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(root) for f in fs if f.endswith(".jpg"))
         sub["e2e"] = {"value": 64 * args.input_batches / sec, "unit": "frames/s", "h2d_bytes_per_step": 64 * (w * h * 3 + A.PLAN_BYTES),
                       "d2h_bytes_per_step": 4, "steps": args.input_batches,
-                      "note": "ImagePairDataLoader.get_dataset(32): JPEG files (%d KB each) -> PIL decode on %d host threads -> pinned "
+                      "note": "ImagePairDataLoader.get_dataset(32): JPEG files (%d KB each) -> PIL decode in %d worker processes -> shared pinned "
                               "staging -> H2D -> one kp_augment_frames launch per batch of 64 frames; bound by the host JPEG decode"
                               % (jpeg // (8 * 24) >> 10, _host_threads())}
+        if args.input_train_steps > 0:
+            sub["train_from_files"] = _train_from_files(args, dev, root)
         names = open(os.path.join(root, "train_set.txt")).read().splitlines()
         rnd = random.Random(0)
         t0, pairs = time.perf_counter(), 0
@@ -754,6 +805,13 @@ def run_ours(args):
             os._exit(0)
         return
 
+    if args.workload == "input":
+        if rank == 0:
+            sub = bench_input(args, dev, lib, peaks)
+            sub.update({"metric": "input-pipeline frames/sec (kp_augment_frames)", "value": sub["frames_per_s"], "unit": "frames/s",
+                        "n_gpus": 1, "higher_is_better": True, "data": "synthetic", "config": {"workload": sub["workload"]}})
+            emit(sub)
+        return
     if args.workload in ("pseudo", "render", "fwd8"):
         line = measure_inference(args.workload, args, world, rank, dev, lib, peaks, args.steps, args.warmup)
         if rank == 0:
@@ -951,7 +1009,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="train", choices=["train", "k1", "pseudo", "render", "fwd8"])
+    ap.add_argument("--workload", default="train", choices=["train", "k1", "pseudo", "render", "fwd8", "input"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="train: pairs per GPU per run")
     ap.add_argument("--frames", type=int, default=1024, help="k1: frames per GPU per launch")
@@ -961,6 +1019,7 @@ def main():
     ap.add_argument("--fwd-pairs", type=int, default=8, help="fwd8: frame pairs per call")
     ap.add_argument("--input-frames", type=int, default=2048, help="input: decoded frames per launch")
     ap.add_argument("--input-batches", type=int, default=20, help="input: loader batches (32 pairs) timed end to end")
+    ap.add_argument("--input-train-steps", type=int, default=20, help="input: train steps fed from JPEG files (0 = skip)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="cpu_baseline of the CUDA arm: oracle train step at this batch")
     ap.add_argument("--cpu-budget", type=int, default=100, help="--impl reference: seconds of timed CPU steps")
     ap.add_argument("--no-graph", action="store_true")

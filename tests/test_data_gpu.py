@@ -55,8 +55,8 @@ def test_every_enhancement_factor(cuda_dev):
             assert np.array_equal(g, DC.oracle_frame(f, r)), r
 
 
-@pytest.mark.parametrize("prefetch", [False, True])
-def test_pair_loader_reproduces_the_reference_stream(cuda_dev, tmp_path, prefetch):
+@pytest.mark.parametrize("prefetch,decode", [(False, "thread"), (True, "process"), (False, "process")])
+def test_pair_loader_reproduces_the_reference_stream(cuda_dev, tmp_path, prefetch, decode):
     """Seeded like the fixture generator, ImagePairDataLoader.get_dataset yields the reference's batches bit for bit."""
     from kp_b200 import data
     fx = DC.fixture()
@@ -64,7 +64,8 @@ def test_pair_loader_reproduces_the_reference_stream(cuda_dev, tmp_path, prefetc
     np.random.seed(DC.SEED)
     random.seed(DC.SEED)
     ld = data.ImagePairDataLoader(root, "train", random_order=True, randomness=True)
-    ds = ld.get_dataset(batch_size=4, repeat=True, num_preprocess_threads=4, prefetch=prefetch, device=cuda_dev)
+    ds = ld.get_dataset(batch_size=4, repeat=True, num_preprocess_threads=4, prefetch=prefetch, device=cuda_dev,
+                        decode=decode)
     n, k = len(fx["train_sha256_f32"]), 0
     for batch in ds:
         assert batch["image"].shape == (4, 128, 128, 3) and batch["image"].dtype == torch.float32 and batch["image"].is_cuda
@@ -78,7 +79,8 @@ def test_pair_loader_reproduces_the_reference_stream(cuda_dev, tmp_path, prefetc
     assert k == (n // 4) * 4
     ld = data.ImagePairDataLoader(root, "test", random_order=False, randomness=False)
     from oracle import pil_ops as O
-    got = list(ld.get_dataset(batch_size=4, prefetch=prefetch, device=cuda_dev))
+    ds.close()
+    got = list(ld.get_dataset(batch_size=4, prefetch=prefetch, device=cuda_dev, decode=decode))
     assert [b["image"].shape[0] for b in got] == [4, 2]                 # ragged last batch
     torch.cuda.synchronize()
     im = np.concatenate([b["image"].cpu().numpy() for b in got])

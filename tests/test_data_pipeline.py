@@ -182,3 +182,31 @@ def test_keypoint_loader_descriptions_reproduce_the_reference(lib_built, tmp_pat
         got = DC.emulate([_decode(r["path"]) if not r.get("zero") else None for r in reqs], reqs)
         assert np.array_equal(got[:n], real)
         assert DC.sha(got) == str(fx["kp_sha256_f32"][v])
+
+
+def test_decode_workers_write_identical_bytes_and_surface_errors(lib_built, tmp_path):
+    """The worker processes of the loader (data/_kp_decode_worker.py) decode into a shared staging file exactly what PIL
+    decodes in-process; a failing file raises in the parent."""
+    import mmap
+    from kp_b200.data import base_dataloader as BD
+    root = DC.lay_out_dataset(tmp_path)
+    paths = [str(tmp_path / "frames" / "0001" / ("%06d.jpg" % i)) for i in (1, 2, 3)] + \
+            [str(tmp_path / "frames" / "0002" / "000001.jpg")]
+    sizes = [BD.jpeg_size(p) for p in paths]
+    offs = np.cumsum([0] + [w * h * 3 for w, h in sizes])
+    stage = str(tmp_path / "stage_1")
+    with open(stage, "w+b") as fh:
+        fh.truncate(int(offs[-1]))
+        view = np.frombuffer(mmap.mmap(fh.fileno(), int(offs[-1])), np.uint8)
+    W = BD._DecodeWorkers(2)
+    try:
+        W.run([(stage, int(offs[i]), p) + tuple(sizes[i]) for i, p in enumerate(paths)])
+        for i, p in enumerate(paths):
+            w, h = sizes[i]
+            assert np.array_equal(view[offs[i]:offs[i + 1]].reshape(h, w, 3), BD.decode_rgb(p))
+        with pytest.raises(RuntimeError, match="decode worker"):
+            W.run([(stage, 0, str(tmp_path / "missing.jpg"), 4, 4)])
+        with pytest.raises(RuntimeError, match="header said"):
+            W.run([(stage, 0, paths[0], 5, 5)])
+    finally:
+        W.close()

@@ -125,17 +125,35 @@ KP_HD uint8_t blend_px(int deg, int img, float alpha) {     // Blend.c
 }
 
 // ---- phase 1: gather crop rows band*32-2 .. band*32+33 into the tile ------------------------------------------------------
+// Latency-bound if done pixel by pixel: the indices of GATHER_UNROLL pixels are computed first, then all their loads are
+// issued, then the tile is written.
+constexpr int GATHER_UNROLL = 6;
 KP_HD void phase_gather(const uint8_t* src, const kp_frame_plan& plan, int band, uint8_t* tile, int tid, int nthr) {
     const int row0 = band * BAND - HALO;
-    for (int i = tid; i < ROWS * S; i += nthr) {
-        const int r = i / S, x = i - r * S, y = row0 + r;
-        uint8_t v0 = 0, v1 = 0, v2 = 0;
-        long long idx;
-        if (y >= 0 && y < S && source_index(plan, plan.ytab[y], plan.xtab[x], &idx)) {
-            v0 = src[idx], v1 = src[idx + 1], v2 = src[idx + 2];
+    for (int base = tid; base < ROWS * S; base += nthr * GATHER_UNROLL) {
+        long long idx[GATHER_UNROLL];
+        uint8_t v[GATHER_UNROLL][3];
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+            const int i = base + u * nthr;
+            const int r = i / S, x = i - r * S, y = row0 + r;
+            idx[u] = -1;
+            long long t;
+            if (i < ROWS * S && y >= 0 && y < S && source_index(plan, plan.ytab[y], plan.xtab[x], &t)) idx[u] = t;
         }
-        uint8_t* t = tile + r * ROWB + x * 3;
-        t[0] = v0, t[1] = v1, t[2] = v2;
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+            v[u][0] = v[u][1] = v[u][2] = 0;
+            if (idx[u] >= 0) v[u][0] = src[idx[u]], v[u][1] = src[idx[u] + 1], v[u][2] = src[idx[u] + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+            const int i = base + u * nthr;
+            if (i < ROWS * S) {
+                uint8_t* t = tile + i * 3;              // (i / S) * ROWB + (i % S) * 3
+                t[0] = v[u][0], t[1] = v[u][1], t[2] = v[u][2];
+            }
+        }
     }
 }
 

@@ -6,17 +6,27 @@ files, and what the drawn rotation / crop / flip / filter are - and ``DeviceData
 device tensors:
 
     main (or prefetch) thread : pull descriptions (random draws in the reference's order, image sizes from JPEG headers)
-    decode pool (12 threads)  : PIL decodes each JPEG straight into a pinned uint8 staging buffer (GIL released)
+    decode workers (12)       : PIL decodes each JPEG straight into the batch's staging buffer - worker PROCESSES writing
+                                into a shared mapping that is registered with CUDA as pinned memory (PIL's JPEG plugin
+                                holds the GIL for its Python-level parsing, threads do not scale), or threads
     side CUDA stream          : H2D of frames + plans, ONE kp_augment_frames launch -> float32 [n,128,128,3] in [-1,1]
     consumer                  : current stream waits on the batch's event
 
 A frame request is a dict: ``path`` (or ``zero``), ``size`` (w, h of the JPEG), ``resize`` (W, H), ``crop`` (left, top),
 ``angle``, ``flip``, ``filter_id``, ``factor``.
 """
+import atexit
 import collections
 import concurrent.futures
+import mmap
+import os
+import pickle
 import queue
 import random
+import struct
+import subprocess
+import sys
+import tempfile
 import threading
 from abc import ABC, abstractmethod
 
@@ -38,6 +48,26 @@ def zero_frame():
     return {"zero": True}
 
 
+_DIR_LEN, _JPEG_SIZE = {}, {}
+
+
+def dir_len(folder):
+    """len(os.listdir(folder)) (image_pair_dataloader.py:74), remembered: a video's frame count does not change."""
+    n = _DIR_LEN.get(folder)
+    if n is None:
+        n = _DIR_LEN[folder] = len(os.listdir(folder))
+    return n
+
+
+def jpeg_size(path):
+    """(w, h) from the JPEG header, remembered per file (the reference reads it from the opened image, :95)."""
+    s = _JPEG_SIZE.get(path)
+    if s is None:
+        with Image.open(path) as im:
+            s = _JPEG_SIZE[path] = im.size
+    return s
+
+
 def decode_rgb(path):
     """The decoded frame as uint8 [h, w, 3] (the reference hands PIL's decode to ``np.asarray`` as is)."""
     with Image.open(path) as im:
@@ -45,31 +75,118 @@ def decode_rgb(path):
 
 
 class _Staging:
-    """One batch in flight: pinned frame bytes + plans, their device copies, the output tensor and the done event."""
+    """One batch in flight: frame bytes + plans in a shared, CUDA-registered host mapping (decode workers write into it),
+    their device copy, and the event that marks the batch's kernel."""
+    _count = [0]
 
     def __init__(self, device):
         self.device = device
-        self.host = None
-        self.dev = None
-        self.event = None
+        self.host = self.dev = self.event = self.path = self._mm = None
+        self._registered = False
+        _Staging._count[0] += 1
+        self._stem = "kp_b200_stage_%d_%d" % (os.getpid(), _Staging._count[0])
+        self._gen = 0
 
     def reserve(self, nbytes):
         if self.host is None or self.host.numel() < nbytes:
+            self.release()
             cap = max(int(nbytes * 1.25), 1 << 20)
-            self.host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+            self._gen += 1
+            self.path = os.path.join(shm, "%s_%d" % (self._stem, self._gen))
+            with open(self.path, "w+b") as fh:
+                fh.truncate(cap)
+                self._mm = mmap.mmap(fh.fileno(), cap)
+            self.host = torch.frombuffer(self._mm, dtype=torch.uint8)
+            rc = torch.cuda.cudart().cudaHostRegister(self.host.data_ptr(), cap, 0)
+            self._registered = int(rc) == 0
+            self._pinned = None if self._registered else torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
         return self.host
+
+    def upload_source(self, nbytes):
+        """The host tensor to copy from: the registered mapping itself, or a pinned bounce buffer if registering failed."""
+        if self._registered:
+            return self.host
+        self._pinned[:nbytes].copy_(self.host[:nbytes])
+        return self._pinned
+
+    def release(self):
+        if self.host is not None:
+            if self.event is not None:
+                self.event.synchronize()
+            if self._registered:
+                try:
+                    torch.cuda.cudart().cudaHostUnregister(self.host.data_ptr())
+                except Exception:          # interpreter / context teardown
+                    pass
+            self.host = None
+        if self.path is not None:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+            self.path = None
+
+
+class _DecodeWorkers:
+    """Plain subprocesses running data/_kp_decode_worker.py (numpy + PIL only; never CUDA)."""
+
+    def __init__(self, n):
+        script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_kp_decode_worker.py")
+        self.procs = [subprocess.Popen([sys.executable, script], stdin=subprocess.PIPE, stdout=subprocess.PIPE)
+                      for _ in range(n)]
+        atexit.register(self.close)
+
+    def run(self, tasks):
+        """tasks: list of (staging file, offset, path, w, h), dealt round-robin; raises on the first worker error."""
+        used = []
+        for i, p in enumerate(self.procs):
+            part = tasks[i::len(self.procs)]
+            if part:
+                blob = pickle.dumps(part)
+                p.stdin.write(struct.pack("<I", len(blob)) + blob)
+                p.stdin.flush()
+                used.append(p)
+        err = None
+        for p in used:
+            hdr = p.stdout.read(4)
+            if len(hdr) < 4:
+                raise RuntimeError("a decode worker died (exit code %r)" % p.poll())
+            err = pickle.loads(p.stdout.read(struct.unpack("<I", hdr)[0])) or err
+        if err:
+            raise RuntimeError("decode worker: " + err)
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.close()
+            except OSError:
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        self.procs = []
 
 
 class DeviceDataset:
     """Iterable of batches ``{key: CUDA tensor}``; what ``BaseDataLoader.get_dataset`` returns."""
 
-    def __init__(self, loader, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device, shuffle_buffer=2000):
+    def __init__(self, loader, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device, shuffle_buffer=2000,
+                 decode="process"):
         if not torch.cuda.is_available():
             raise RuntimeError("the input pipeline augments on the GPU; there is no CPU path")
+        if decode not in ("process", "thread"):
+            raise ValueError("decode must be 'process' or 'thread'")
         self.loader, self.batch_size, self.repeat, self.shuffle = loader, int(batch_size), repeat, shuffle
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.pool = concurrent.futures.ThreadPoolExecutor(max(1, int(num_preprocess_threads)))
+        self.n_workers = max(1, min(int(num_preprocess_threads), os.cpu_count() or 1))
+        self.decode = decode
+        self.pool = concurrent.futures.ThreadPoolExecutor(self.n_workers)
+        self.workers = None
+        self._slots = []
         self.prefetch = 1 if prefetch else 0
         self.stream = torch.cuda.Stream(device=self.device)
         self.shuffle_buffer = shuffle_buffer
@@ -110,24 +227,31 @@ class DeviceDataset:
         host = slot.reserve(total + plan_bytes + 16)
         host_np = host.numpy()
 
-        def work(i):
-            r = reqs[i]
+        live = [i for i in range(n) if not reqs[i].get("zero")]
+        if self.decode == "process":
+            if self.workers is None:
+                self.workers = _DecodeWorkers(self.n_workers)
+            self.workers.run([(slot.path, offs[i], reqs[i]["path"]) + tuple(reqs[i]["size"]) for i in live])
+        else:
+            def work(i):
+                w, h = reqs[i]["size"]
+                px = decode_rgb(reqs[i]["path"])
+                if px.shape != (h, w, 3):
+                    raise ValueError("%s: decoded %s, header said %s" % (reqs[i]["path"], px.shape, (h, w, 3)))
+                host_np[offs[i]:offs[i] + px.size] = px.reshape(-1)
+
+            list(self.pool.map(work, live))
+        for i, r in enumerate(reqs):
             if r.get("zero"):
                 plans.set_zero(i)
-                return
-            w, h = r["size"]
-            px = decode_rgb(r["path"])
-            if px.shape != (h, w, 3):
-                raise ValueError("%s: decoded %s, header said %s" % (r["path"], px.shape, (h, w, 3)))
-            host_np[offs[i]:offs[i] + px.size] = px.reshape(-1)
-            plans.set(i, offs[i], w, h, r["resize"][0], r["resize"][1], r["crop"][0], r["crop"][1], r["angle"], r["flip"],
-                      r["filter_id"], r["factor"])
-
-        list(self.pool.map(work, range(n)))
+            else:
+                plans.set(i, offs[i], r["size"][0], r["size"][1], r["resize"][0], r["resize"][1], r["crop"][0], r["crop"][1],
+                          r["angle"], r["flip"], r["filter_id"], r["factor"])
         plan_off = (total + 15) // 16 * 16
         host[plan_off:plan_off + plan_bytes].copy_(plans.host[:plan_bytes])
         with torch.cuda.stream(self.stream):
-            slot.dev[:plan_off + plan_bytes].copy_(host[:plan_off + plan_bytes], non_blocking=True)
+            up = slot.upload_source(plan_off + plan_bytes)
+            slot.dev[:plan_off + plan_bytes].copy_(up[:plan_off + plan_bytes], non_blocking=True)
             out = augment.augment_frames(slot.dev, slot.dev[plan_off:plan_off + plan_bytes], n, stream=self.stream)
             slot.event = torch.cuda.Event()
             slot.event.record(self.stream)
@@ -148,6 +272,7 @@ class DeviceDataset:
         if self.shuffle:
             it = self._shuffled(it)
         slots = collections.deque(_Staging(self.device) for _ in range(self.prefetch + 2))
+        self._slots.extend(slots)
         cur = []
         for s in it:
             cur.append(s)
@@ -196,6 +321,21 @@ class DeviceDataset:
         finally:
             stop.set()
 
+    def close(self):
+        """Stop the decode workers and drop the staging mappings (also runs at interpreter exit / garbage collection)."""
+        if self.workers is not None:
+            self.workers.close()
+            self.workers = None
+        for sl in self._slots:
+            sl.release()
+        self._slots = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def _hand_over(self, batch, ev):
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
@@ -229,5 +369,7 @@ class BaseDataLoader(ABC):
         output, so the pipeline does not call this; kept for callers that hold [0,1] tensors."""
         return {k: (v * 2.0 - 1.0 if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in inputs.items()}
 
-    def get_dataset(self, batch_size, repeat=False, shuffle=False, num_preprocess_threads=12, prefetch=True, device=None):
-        return DeviceDataset(self, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device)
+    def get_dataset(self, batch_size, repeat=False, shuffle=False, num_preprocess_threads=12, prefetch=True, device=None,
+                    decode="process"):
+        """``decode``: 'process' (worker processes, the default) or 'thread' (PIL on a thread pool inside this process)."""
+        return DeviceDataset(self, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device, decode=decode)

@@ -1,15 +1,13 @@
 """``ImagePairDataLoader`` (reference: data/image_pair_dataloader.py:16-165): a frame and the frame 8-11 steps later of one
 video, jointly rotated / resized / cropped / flipped / filtered.  The draws come from the global ``numpy.random`` and
 ``random`` generators in the reference's order, so seeding both reproduces the reference's sample stream."""
-import os
 import random
 from os import path as osp
 
 import numpy as np
-from PIL import Image
 
 from ..utils import data as data_utils
-from .base_dataloader import IMAGE_SIZE, BaseDataLoader, frame_request
+from .base_dataloader import IMAGE_SIZE, BaseDataLoader, dir_len, frame_request, jpeg_size
 
 
 class ImagePairDataLoader(BaseDataLoader):
@@ -43,17 +41,14 @@ class ImagePairDataLoader(BaseDataLoader):
         """The description of pair ``idx``: draws in the order of image_pair_dataloader.py:72-150."""
         img_path = self._images[idx].split()[0]
         folder = osp.join(self._data_dir, img_path)
-        file_len = len(os.listdir(folder))
+        file_len = dir_len(folder)
         first, second = 0, 10
         if self._random_order:
             step = random.randint(8, 11)
             first = random.randint(0, file_len - 1)
             second = (first + step) % file_len
         paths = [osp.join(folder, "%06d.jpg" % (i + 1)) for i in (first, second)]
-        sizes = []
-        for p in paths:
-            with Image.open(p) as im:            # header only
-                sizes.append(im.size)
+        sizes = [jpeg_size(p) for p in paths]          # header only
         w, h = sizes[0]
         angle = random.randrange(-10, 11) if self._randomness else 0
         wide = w > h

@@ -1,13 +1,11 @@
 """``KeypointDataLoader`` (reference: data/keypoint_dataloader.py:17-88): every frame of a video, resized and centre-cropped
 by the FIRST frame's geometry, zero frames appended up to 663; ``len`` and ``idx`` ride along (make_pseudo_labels.py:83-101)."""
-import os
 from os import path as osp
 
 import numpy as np
-from PIL import Image
 
 from ..utils import data as data_utils
-from .base_dataloader import IMAGE_SIZE, BaseDataLoader, frame_request, zero_frame
+from .base_dataloader import IMAGE_SIZE, BaseDataLoader, dir_len, frame_request, jpeg_size, zero_frame
 
 MIN_IMAGE_SEQ_LEN = 663
 
@@ -38,12 +36,9 @@ class KeypointDataLoader(BaseDataLoader):
     def _get_image_at(self, idx):
         img_path = self._images[idx].split()[0]
         folder = osp.join(self._data_dir, img_path)
-        file_len = len(os.listdir(folder))
+        file_len = dir_len(folder)
         paths = [osp.join(folder, "%06d.jpg" % (i + 1)) for i in range(file_len)]
-        sizes = []
-        for p in paths:
-            with Image.open(p) as im:
-                sizes.append(im.size)
+        sizes = [jpeg_size(p) for p in paths]
         w, h = sizes[0]
         box, ratio = data_utils.center_crop((w, h), IMAGE_SIZE)
         resize = (int(w / ratio), int(h / ratio))
