@@ -289,6 +289,9 @@ int kp_adam_tf(float* p, const float* g, float* m, float* v, long long n, float 
 int kp_conv1x1_f32(const void* x, const float* w, const float* bias, long long P, int Cin, int Cout, float* out, void* stream);
 /* out[c] += sum over pixels of g bf16 [P,C] (bias gradients). */
 int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream);
+/* out[c] += sum over pixels of g[p,c]^2: with kp_channel_sum the batch statistics of a stand-alone
+ * layers.batch_norm (models/networks/layers.py:13-14) whose input does not come out of a convolution epilogue. */
+int kp_channel_sumsq(const void* g, long long P, int C, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Input pipeline: the per-frame Pillow chain of the reference's loaders on the device

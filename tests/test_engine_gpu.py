@@ -685,3 +685,36 @@ def test_two_layer_chain_forward_backward(cuda_dev, geom):
     _close(ctx.G.g("a/conv2d/kernel"), P["w1"].grad, 1.5e-2, "dW layer 1")
     _close(ctx.G.g("b/conv2d/kernel"), P["w2"].grad, 1e-2, "dW layer 2")
     _close(dx, x64.grad, 1.5e-2, "dX")
+
+
+@pytest.mark.parametrize("C,train", [(16, True), (64, True), (24, True), (32, False)])
+def test_standalone_batch_norm_layer(cuda_dev, C, train):
+    """networks.layers.batch_norm (reference layers.py:13-14) as a stand-alone op: batch statistics from kp_channel_sum /
+    kp_channel_sumsq (no torch reductions), biased variance for the normalisation, unbiased for the moving average."""
+    from kp_b200 import networks
+    from kp_b200.networks import layers
+    rng = np.random.default_rng(C)
+    N, H, W = 3, 10, 12
+    x = torch.from_numpy(rng.normal(0.5, 2.0, (N, H, W, C)).astype(np.float32)).to(BF)
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32))
+    beta = torch.from_numpy(rng.normal(0, 0.3, C).astype(np.float32))
+    mm0 = torch.from_numpy(rng.normal(0, 0.2, C).astype(np.float32))
+    mv0 = torch.from_numpy(rng.uniform(0.5, 2.0, C).astype(np.float32))
+    ctx = _mk_ctx(cuda_dev, {}, bn={"bn": C})
+    ctx.G.p("bn/gamma").copy_(gamma); ctx.G.p("bn/beta").copy_(beta)
+    ctx.S.p("bn/moving_mean").copy_(mm0); ctx.S.p("bn/moving_variance").copy_(mv0)
+    ctx.update_moving = True
+    networks.set_context(ctx)
+    y = layers.batch_norm(x.to(cuda_dev), train, scope="bn")
+    torch.cuda.synchronize()
+    xd = x.double()
+    if train:
+        mean, var = xd.mean(dim=(0, 1, 2)), xd.var(dim=(0, 1, 2), unbiased=False)
+        n = N * H * W
+        assert torch.allclose(ctx.S.p("bn/moving_mean").cpu().double(), mm0.double() * 0.999 + mean * 0.001, atol=1e-5)
+        assert torch.allclose(ctx.S.p("bn/moving_variance").cpu().double(), mv0.double() * 0.999 + var * n / (n - 1) * 0.001,
+                              atol=1e-5)
+    else:
+        mean, var = mm0.double(), mv0.double()
+    ref = (xd - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    _close(y, ref, 1e-2, "batch_norm out")

@@ -55,6 +55,7 @@ SIGNATURES = {
     "kp_bce_logits_fwd_bwd": [c_vp, c_int, c_float, c_float, c_vp, c_vp, c_vp],
     "kp_adam_tf": [c_vp, c_vp, c_vp, c_vp, c_ll, c_float, c_float, c_float, c_float, c_int, c_float, c_vp, c_vp],
     "kp_channel_sum": [c_vp, c_ll, c_int, c_vp, c_vp],
+    "kp_channel_sumsq": [c_vp, c_ll, c_int, c_vp, c_vp],
     "kp_conv1x1_f32": [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp, c_vp],
     "kp_pack_weights": [c_vp, c_vp, c_vp, c_vp, c_vp],
     "kp_pack_job_blocks": [c_vp],

@@ -843,6 +843,8 @@ __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ 
 }
 
 // per-channel sum over pixels of a bf16 [P,C] tensor (bias gradients of non-BN layers): out[c] += sum_p g[p,c]
+// (SQ: sum of squares - the second batch-norm statistic of the stand-alone layers.batch_norm)
+template <bool SQ>
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const __nv_bfloat16* __restrict__ g, long long P, int C, float* __restrict__ out) {
     const int CG = C >> 3;
@@ -853,7 +855,7 @@ channel_sum_kernel(const __nv_bfloat16* __restrict__ g, long long P, int C, floa
         float t[8];
         bf8_unpack(*reinterpret_cast<const uint4*>(g + p * C + cg * 8), t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] += t[j];
+        for (int j = 0; j < 8; ++j) s[j] += SQ ? t[j] * t[j] : t[j];
     }
     // tree reduction (shuffles when the channel groups tile a warp, shared-memory atomics across warps, one global atomic
     // per channel per block) - the serial walk by pixel lane 0 cost 36 us per call for C = 8
@@ -1080,11 +1082,14 @@ int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float 
     KP_LAUNCHED();
     return KP_OK;
 }
-int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st) {
+int ew_channel_sum(const void* g, long long P, int C, float* out, int squares, cudaStream_t st) {
     KP_REQUIRE(C % 8 == 0 && C / 8 <= 256, "channel_sum: C=%d must be a multiple of 8, at most 2048", C);
     const int lanes = 256 / (C / 8);
-    channel_sum_kernel<<<grid_for((P + lanes - 1) / lanes, 1, 148 * 4), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g),
-                                                                                       P, C, out);
+    const int grid = grid_for((P + lanes - 1) / lanes, 1, 148 * 4);
+    if (squares)
+        channel_sum_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), P, C, out);
+    else
+        channel_sum_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g), P, C, out);
     KP_LAUNCHED();
     return KP_OK;
 }

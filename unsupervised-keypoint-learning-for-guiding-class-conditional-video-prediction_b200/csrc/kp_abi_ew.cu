@@ -155,7 +155,13 @@ int kp_channel_sum(const void* g, long long P, int C, float* out, void* stream) 
     KP_NONNEG(P);
     if (P == 0) return KP_OK;
     KP_NONNULL(g); KP_NONNULL(out);
-    return ew_channel_sum(g, P, C, out, ST);
+    return ew_channel_sum(g, P, C, out, 0, ST);
+}
+int kp_channel_sumsq(const void* g, long long P, int C, float* out, void* stream) {
+    KP_NONNEG(P);
+    if (P == 0) return KP_OK;
+    KP_NONNULL(g); KP_NONNULL(out);
+    return ew_channel_sum(g, P, C, out, 1, ST);
 }
 
 }  // extern "C"

@@ -89,7 +89,7 @@ int ew_l1_pair(const void* feat_gt, const void* feat_pred, long long half_elems,
 int ew_bce_logits(const float* x, int n, float z, float weight, float* loss, void* d_logits, cudaStream_t st);
 int ew_adam_tf(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int t,
                float grad_scale, const float* lr_t_dev, cudaStream_t st);
-int ew_channel_sum(const void* g, long long P, int C, float* out, cudaStream_t st);
+int ew_channel_sum(const void* g, long long P, int C, float* out, int squares, cudaStream_t st);
 int ew_pack_job_blocks(const kp_pack_desc* d);
 int ew_pack_weights_batch(const void* jobs_dev, int n_jobs, int total_blocks, cudaStream_t st);
 int ew_pack_weights(const float* w, const kp_pack_desc* d, const float* row_scale, void* dst, cudaStream_t st);

@@ -37,9 +37,9 @@ def batch_norm(x, train_mode, scope='batch_norm'):
     N, H, W, C = x.shape
     gamma, beta = ctx.p(scope + "/gamma"), ctx.p(scope + "/beta")
     if train_mode:
-        xf = x.float()   # stand-alone path only (not used by the fused builders): statistics via torch reductions
-        ssum = xf.sum(dim=(0, 1, 2)).contiguous()
-        ssq = (xf * xf).sum(dim=(0, 1, 2)).contiguous()
+        # stand-alone path (the fused builders take the statistics from the convolution epilogue instead)
+        stats = torch.zeros((2, C), device=x.device, dtype=torch.float32)
+        ssum, ssq = ops.channel_sum(x, stats[0]), ops.channel_sum(x, stats[1], squares=True)
         mm = ctx.p(scope + "/moving_mean") if ctx.update_moving else None
         mv = ctx.p(scope + "/moving_variance") if ctx.update_moving else None
         scale, shift, _, _ = ops.bn_finalize(ssum, ssq, None, gamma, beta, N * H * W, mm, mv)

@@ -221,7 +221,8 @@ def adam_tf(p, g, m, v, lr, t, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0,
               _p(lr_t_dev), _st())
 
 
-def channel_sum(g, out):
+def channel_sum(g, out, squares=False):
+    """out[c] += sum over pixels of g[...,c] (squares: of g[...,c]**2)."""
     C = g.shape[-1]
-    _lib.call("kp_channel_sum", _p(g), g.numel() // C, C, _p(out), _st())
+    _lib.call("kp_channel_sumsq" if squares else "kp_channel_sum", _p(g), g.numel() // C, C, _p(out), _st())
     return out
