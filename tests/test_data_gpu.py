@@ -1,5 +1,6 @@
 """GPU: the input pipeline through the C ABI - byte-exact against the oracle and against what the
 unmodified reference loaders produced (tests/golden/data_reference.npz)."""
+import os
 import random
 
 import numpy as np
@@ -114,3 +115,28 @@ def test_loader_feeds_the_train_step(cuda_dev, tmp_path):
     model.build(next(it))
     lD, lG, _, bs = model.test_step()
     assert np.isfinite(lD) and np.isfinite(lG) and bs == 2
+
+
+def test_pseudo_labels_from_the_keypoint_loader(cuda_dev, tmp_path):
+    """make_pseudo_labels.py end to end: KeypointDataLoader -> KeypointModel -> pseudo_labels/{idx:04d}.npy, sharded over two
+    (simulated) ranks; each file holds the detector's key points of exactly the `len` real frames of its video."""
+    from kp_b200 import data, models
+    fx = DC.fixture()
+    root = DC.lay_out_dataset(tmp_path / "data")
+    cfg = {"paths": {"data_dir": root, "vggnet": None, "log_dir": str(tmp_path / "log")},
+           "model": {"n_pts": 40, "n_action": 9, "cell_info": [1024, 1024], "vae_dim": 64}}
+    model = models.KeypointModel(cfg, device=cuda_dev)
+    kl = data.KeypointDataLoader(root, "test")
+    out = str(tmp_path / "pseudo_labels")
+    files = []
+    for rank in (0, 1):
+        files += model.write_pseudo_labels(kl, out, rank=rank, world=2)
+    assert sorted(np.unique(files)) == sorted(files) and len(files) == 6
+    videos = list(kl.get_dataset(1, device=cuda_dev))
+    for v in videos:
+        idx, n = int(v["idx"][0]), int(v["len"][0])
+        arr = np.load(os.path.join(out, "%04d.npy" % idx))          # what data/sequence_dataloader.py:101 reads
+        assert arr.dtype == np.float32 and arr.shape == (n, 40, 2) and n == int(fx["kp_len"][list(fx["kp_idx"]).index(idx)])
+        want = model.detect(v["image"][0, :n].contiguous()).cpu().numpy()
+        assert np.array_equal(arr, want)
+        assert np.all(np.abs(arr) <= 1.0)

@@ -175,7 +175,7 @@ class DeviceDataset:
     """Iterable of batches ``{key: CUDA tensor}``; what ``BaseDataLoader.get_dataset`` returns."""
 
     def __init__(self, loader, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device, shuffle_buffer=2000,
-                 decode="process"):
+                 decode="process", sample_range=None):
         if not torch.cuda.is_available():
             raise RuntimeError("the input pipeline augments on the GPU; there is no CPU path")
         if decode not in ("process", "thread"):
@@ -184,6 +184,7 @@ class DeviceDataset:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.n_workers = max(1, min(int(num_preprocess_threads), os.cpu_count() or 1))
         self.decode = decode
+        self.sample_range = sample_range
         self.pool = concurrent.futures.ThreadPoolExecutor(self.n_workers)
         self.workers = None
         self._slots = []
@@ -196,7 +197,10 @@ class DeviceDataset:
     # -- sample stream -------------------------------------------------------------------------------------------------
     def _samples(self):
         while True:
-            yield from self.loader.sample_generator()
+            if self.sample_range is None:
+                yield from self.loader.sample_generator()
+            else:
+                yield from self.loader.sample_generator(*self.sample_range)
             if not self.repeat:
                 return
 
@@ -370,6 +374,8 @@ class BaseDataLoader(ABC):
         return {k: (v * 2.0 - 1.0 if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in inputs.items()}
 
     def get_dataset(self, batch_size, repeat=False, shuffle=False, num_preprocess_threads=12, prefetch=True, device=None,
-                    decode="process"):
-        """``decode``: 'process' (worker processes, the default) or 'thread' (PIL on a thread pool inside this process)."""
-        return DeviceDataset(self, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device, decode=decode)
+                    decode="process", sample_range=None):
+        """``decode``: 'process' (worker processes, the default) or 'thread' (PIL on a thread pool inside this process).
+        ``sample_range`` = (start, stop): forwarded to ``sample_generator`` by loaders that shard (KeypointDataLoader)."""
+        return DeviceDataset(self, batch_size, repeat, shuffle, num_preprocess_threads, prefetch, device, decode=decode,
+                             sample_range=sample_range)

@@ -29,8 +29,9 @@ class KeypointDataLoader(BaseDataLoader):
     def get_sample_dtype(self):
         return {"image": np.float32, "len": np.int16, "idx": np.int16}
 
-    def sample_generator(self):
-        for idx in range(self._total):
+    def sample_generator(self, start=0, stop=None):
+        """All videos in list order (the reference); ``start`` / ``stop`` restrict it to one rank's shard."""
+        for idx in range(start, self._total if stop is None else min(stop, self._total)):
             yield self._get_image_at(idx)
 
     def _get_image_at(self, idx):

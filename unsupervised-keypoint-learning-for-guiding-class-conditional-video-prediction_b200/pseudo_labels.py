@@ -78,15 +78,17 @@ def write_pseudo_labels(detect, videos, out_dir, rank=None, world=None):
 
     videos: sequence of dicts {'image': [T,128,128,3] or [1,T,128,128,3] float tensor in [-1,1], 'idx': int, 'len': int}
             (the reference's keypoint_dataloader.py:33-38 element: 'len' real frames, the rest zero padding) or a callable
-            i -> such a dict plus `n` via len().
+            i -> such a dict plus `n` via len(); or a `data.KeypointDataLoader` (make_pseudo_labels.py:55-66): this rank's shard
+            of its video list is then decoded and cropped by the loader's device pipeline, one video per batch.
     Returns the list of files this rank wrote."""
     rank = dp.rank() if rank is None else rank
     world = dp.world_size() if world is None else world
-    lo, hi = dp.shard_range(len(videos), rank, world)
+    from_loader = hasattr(videos, "get_dataset")
+    lo, hi = dp.shard_range(videos.length() if from_loader else len(videos), rank, world)
     writer = PseudoLabelWriter(out_dir)
+    dataset = videos.get_dataset(1, sample_range=(lo, hi)) if from_loader and hi > lo else None
     try:
-        for i in range(lo, hi):
-            v = videos[i]
+        for v in (dataset if from_loader else (videos[i] for i in range(lo, hi))) or ():
             im = v['image']
             if im.dim() == 5:
                 im = im[0]
@@ -96,4 +98,6 @@ def write_pseudo_labels(detect, videos, out_dir, rank=None, world=None):
             writer.put(idx, pts)
     finally:
         files = writer.close()
+        if dataset is not None:
+            dataset.close()
     return files
