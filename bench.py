@@ -665,12 +665,13 @@ def _train_from_files(args, dev, root):
     cfg["training"]["batch_size"] = B
     np.random.seed(1); random.seed(1)
     ld = data.ImagePairDataLoader(root, "train", random_order=True, randomness=True)
-    ds = ld.get_dataset(batch_size=B, repeat=True, shuffle=True, num_preprocess_threads=_host_threads(), prefetch=True, device=dev)
+    workers = int(os.environ.get("KP_INPUT_WORKERS", str(_host_threads())))   # capped by the loader at cores - 2
+    ds = ld.get_dataset(batch_size=B, repeat=True, shuffle=True, num_preprocess_threads=workers, prefetch=True, device=dev)
     it = iter(ds)
     model = models.DetectorTranslatorModel(cfg, is_training=True, device=dev, seed=0)
     model.build(lambda: next(it))
     model.enable_cuda_graph(B)
-    for _ in range(3):
+    for _ in range(8):
         model.train_step()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -682,8 +683,8 @@ def _train_from_files(args, dev, root):
     model._graph = None
     return {"value": 4 * B * args.input_train_steps / sec, "unit": "frames/s", "ms_per_step": sec / args.input_train_steps * 1e3,
             "steps": args.input_train_steps,
-            "note": "train_step at batch %d fed by ImagePairDataLoader.get_dataset (JPEG decode in worker processes, augmentation "
-                    "kernel, shuffle buffer) - two batches per step, losses D2H every step" % B}
+            "note": "train_step at batch %d fed by ImagePairDataLoader.get_dataset (JPEG decode in %d worker processes, augmentation "
+                    "kernel, shuffle buffer) - two batches per step, losses D2H every step" % (B, ds.n_workers)}
 
 
 def bench_input(args, dev, lib, peaks):
@@ -764,7 +765,7 @@ def bench_input(args, dev, lib, peaks):
                       "d2h_bytes_per_step": 4, "steps": args.input_batches,
                       "note": "ImagePairDataLoader.get_dataset(32): JPEG files (%d KB each) -> PIL decode in %d worker processes -> shared pinned "
                               "staging -> H2D -> one kp_augment_frames launch per batch of 64 frames; bound by the host JPEG decode"
-                              % (jpeg // (8 * 24) >> 10, _host_threads())}
+                              % (jpeg // (8 * 24) >> 10, ds.n_workers)}
         if args.input_train_steps > 0:
             sub["train_from_files"] = _train_from_files(args, dev, root)
         names = open(os.path.join(root, "train_set.txt")).read().splitlines()
@@ -1019,7 +1020,7 @@ def main():
     ap.add_argument("--fwd-pairs", type=int, default=8, help="fwd8: frame pairs per call")
     ap.add_argument("--input-frames", type=int, default=2048, help="input: decoded frames per launch")
     ap.add_argument("--input-batches", type=int, default=20, help="input: loader batches (32 pairs) timed end to end")
-    ap.add_argument("--input-train-steps", type=int, default=20, help="input: train steps fed from JPEG files (0 = skip)")
+    ap.add_argument("--input-train-steps", type=int, default=40, help="input: train steps fed from JPEG files (0 = skip)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="cpu_baseline of the CUDA arm: oracle train step at this batch")
     ap.add_argument("--cpu-budget", type=int, default=100, help="--impl reference: seconds of timed CPU steps")
     ap.add_argument("--no-graph", action="store_true")

@@ -182,7 +182,8 @@ class DeviceDataset:
             raise ValueError("decode must be 'process' or 'thread'")
         self.loader, self.batch_size, self.repeat, self.shuffle = loader, int(batch_size), repeat, shuffle
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.n_workers = max(1, min(int(num_preprocess_threads), os.cpu_count() or 1))
+        # decode workers: what the caller asked for, leaving two cores to the consumer and the batch-building thread
+        self.n_workers = max(1, min(int(num_preprocess_threads), (os.cpu_count() or 3) - 2))
         self.decode = decode
         self.sample_range = sample_range
         self.pool = concurrent.futures.ThreadPoolExecutor(self.n_workers)
