@@ -666,6 +666,10 @@ def _train_from_files(args, dev, root):
     np.random.seed(1); random.seed(1)
     ld = data.ImagePairDataLoader(root, "train", random_order=True, randomness=True)
     workers = int(os.environ.get("KP_INPUT_WORKERS", str(_host_threads())))   # capped by the loader at cores - 2
+    # the loader's batch-building thread and this thread share the GIL: a short switch interval keeps the step's launches
+    # from waiting the default 5 ms behind it
+    old_interval = sys.getswitchinterval()
+    sys.setswitchinterval(float(os.environ.get("KP_SWITCH_INTERVAL", "0.0005")))
     ds = ld.get_dataset(batch_size=B, repeat=True, shuffle=True, num_preprocess_threads=workers, prefetch=True, device=dev)
     it = iter(ds)
     model = models.DetectorTranslatorModel(cfg, is_training=True, device=dev, seed=0)
@@ -681,6 +685,7 @@ def _train_from_files(args, dev, root):
     sec = time.perf_counter() - t0
     ds.close()
     model._graph = None
+    sys.setswitchinterval(old_interval)
     return {"value": 4 * B * args.input_train_steps / sec, "unit": "frames/s", "ms_per_step": sec / args.input_train_steps * 1e3,
             "steps": args.input_train_steps,
             "note": "train_step at batch %d fed by ImagePairDataLoader.get_dataset (JPEG decode in %d worker processes, augmentation "

@@ -324,6 +324,12 @@ int kp_augment_plan_host(kp_frame_plan* plan, long long src_offset, int src_w, i
                          double crop_left, double crop_top, int angle_deg, int flip, int filter_id, double factor);
 /* HOST function: the plan of one zero frame of the keypoint loader's padding (data/keypoint_dataloader.py:77-80). */
 int kp_augment_plan_zero_host(kp_frame_plan* plan);
+/* HOST function: n plans in one call from parallel arrays (zero[i] != 0: a zero frame, the other fields of i are ignored);
+ * what a loader calls once per batch.                                                                               */
+int kp_augment_plan_batch_host(kp_frame_plan* plans, int n, const long long* src_offset, const int* src_w, const int* src_h,
+                               const int* resize_w, const int* resize_h, const double* crop_left, const double* crop_top,
+                               const int* angle_deg, const int* flip, const int* filter_id, const double* factor,
+                               const int* zero);
 
 /* src: device buffer of decoded frames; plans: DEVICE array [n_frames]; out f32 [n_frames,128,128,3] =
  * float32(pixel / 255.0) * 2 - 1 (`image / 255.0` of data/image_pair_dataloader.py:162-165 followed by map_fn :63-69).

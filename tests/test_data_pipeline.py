@@ -93,6 +93,26 @@ def test_plan_builder_matches_oracle(lib_built):
             assert list(T.view(0).xtab) == [xt[x0 + x] if 0 <= x0 + x < W else -1 for x in range(128)]
 
 
+def test_batched_plan_builder_equals_single_plans(lib_built):
+    from kp_b200 import augment as A
+    rng = np.random.default_rng(9)
+    frames, reqs = DC.random_requests(rng, 23, SIZES)
+    reqs = [dict(r, size=(f.shape[1], f.shape[0])) for f, r in zip(frames, reqs)]
+    reqs.insert(5, {"zero": True})
+    offs = list(range(0, 1000 * len(reqs), 1000))
+    one, many = A.PlanTable(len(reqs), pin=False), A.PlanTable(len(reqs), pin=False)
+    many.set_batch(reqs, offs)
+    for i, r in enumerate(reqs):
+        if r.get("zero"):
+            one.set_zero(i)
+        else:
+            one.set(i, offs[i], r["size"][0], r["size"][1], r["resize"][0], r["resize"][1], r["crop"][0], r["crop"][1], r["angle"],
+                    r["flip"], r["filter_id"], r["factor"])
+    assert bytes(one.host.numpy()) == bytes(many.host.numpy())
+    with pytest.raises(ValueError):
+        many.set_batch(reqs[:-1], offs[:-1])
+
+
 def test_plan_builder_rejects_bad_arguments(lib_built):
     L = lib_built._lib
     h = L.load()
@@ -201,6 +221,14 @@ def test_decode_workers_write_identical_bytes_and_surface_errors(lib_built, tmp_
     W = BD._DecodeWorkers(2)
     try:
         W.run([(stage, int(offs[i]), p) + tuple(sizes[i]) for i, p in enumerate(paths)])
+        for i, p in enumerate(paths):
+            w, h = sizes[i]
+            assert np.array_equal(view[offs[i]:offs[i + 1]].reshape(h, w, 3), BD.decode_rgb(p))
+        # two submissions outstanding (the loader keeps two batches in flight): answered in order
+        view[:] = 0
+        first = W.submit([(stage, int(offs[i]), paths[i]) + tuple(sizes[i]) for i in (0, 1)])
+        second = W.submit([(stage, int(offs[i]), paths[i]) + tuple(sizes[i]) for i in (2, 3)])
+        first(); second()
         for i, p in enumerate(paths):
             w, h = sizes[i]
             assert np.array_equal(view[offs[i]:offs[i + 1]].reshape(h, w, 3), BD.decode_rgb(p))

@@ -65,6 +65,7 @@ SIGNATURES = {
     "kp_augment_plan_host": [c_vp, c_ll, c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.c_double, c_int, c_int, c_int,
                              ctypes.c_double],
     "kp_augment_plan_zero_host": [c_vp],
+    "kp_augment_plan_batch_host": [c_vp, c_int] + [c_vp] * 12,
     "kp_augment_frames": [c_vp, c_vp, c_int, c_vp, c_vp],
 }
 _RESTYPES = {"kp_last_error": ctypes.c_char_p, "kp_launch_count": ctypes.c_ulonglong}

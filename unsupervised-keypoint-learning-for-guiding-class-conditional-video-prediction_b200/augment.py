@@ -45,6 +45,21 @@ class PlanTable:
     def set_zero(self, i):
         _lib.call("kp_augment_plan_zero_host", self._ptr(i))
 
+    def set_batch(self, requests, offsets):
+        """All plans in ONE library call.  requests: frame-request dicts (data/base_dataloader.py: ``size``, ``resize``,
+        ``crop``, ``angle``, ``flip``, ``filter_id``, ``factor``, or ``zero``); offsets: byte offset of each frame."""
+        n = len(requests)
+        if n != self.n:
+            raise ValueError("set_batch: %d requests for a table of %d plans" % (n, self.n))
+        live = [(0, 1, 1, 1, 1, 0.0, 0.0, 0, 0, NO_FILTER, 0.0, 1) if r.get("zero") else
+                (o, r["size"][0], r["size"][1], r["resize"][0], r["resize"][1], r["crop"][0], r["crop"][1], r["angle"],
+                 int(bool(r["flip"])), r["filter_id"], r["factor"], 0) for r, o in zip(requests, offsets)]
+        cols = list(zip(*live)) if live else [()] * 12
+        kinds = (np.int64, np.int32, np.int32, np.int32, np.int32, np.float64, np.float64, np.int32, np.int32, np.int32,
+                 np.float64, np.int32)
+        arrs = [np.ascontiguousarray(c, dtype=k) for c, k in zip(cols, kinds)]
+        _lib.call("kp_augment_plan_batch_host", ctypes.c_void_p(self._base), n, *[a.ctypes.data for a in arrs])
+
     def view(self, i):
         """The i-th plan as a ctypes structure (host memory of this table)."""
         return FramePlan.from_address(self._base + i * PLAN_BYTES)

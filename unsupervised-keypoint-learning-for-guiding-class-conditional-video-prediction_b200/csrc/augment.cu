@@ -169,6 +169,24 @@ int kp_augment_plan_zero_host(kp_frame_plan* plan) {
     return KP_OK;
 }
 
+int kp_augment_plan_batch_host(kp_frame_plan* plans, int n, const long long* src_offset, const int* src_w, const int* src_h,
+                               const int* resize_w, const int* resize_h, const double* crop_left, const double* crop_top,
+                               const int* angle_deg, const int* flip, const int* filter_id, const double* factor,
+                               const int* zero) {
+    KP_REQUIRE(n >= 0, "%s: argument 'n' must be non-negative", __func__);
+    if (n == 0) return KP_OK;
+    KP_REQUIRE(plans && src_offset && src_w && src_h && resize_w && resize_h && crop_left && crop_top && angle_deg && flip &&
+                   filter_id && factor && zero,
+               "%s: NULL argument", __func__);
+    for (int i = 0; i < n; ++i) {
+        const int rc = zero[i] ? kp_augment_plan_zero_host(plans + i)
+                               : kp_augment_plan_host(plans + i, src_offset[i], src_w[i], src_h[i], resize_w[i], resize_h[i],
+                                                      crop_left[i], crop_top[i], angle_deg[i], flip[i], filter_id[i], factor[i]);
+        if (rc != KP_OK) return rc;
+    }
+    return KP_OK;
+}
+
 int kp_augment_frames(const unsigned char* src, const kp_frame_plan* plans, int n_frames, float* out, void* stream) {
     KP_REQUIRE(n_frames >= 0, "%s: argument 'n_frames' must be non-negative", __func__);
     if (n_frames == 0) return KP_OK;

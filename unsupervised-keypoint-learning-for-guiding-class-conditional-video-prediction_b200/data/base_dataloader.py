@@ -140,6 +140,11 @@ class _DecodeWorkers:
 
     def run(self, tasks):
         """tasks: list of (staging file, offset, path, w, h), dealt round-robin; raises on the first worker error."""
+        self.submit(tasks)()
+
+    def submit(self, tasks):
+        """Send the tasks and return a function that waits for them.  Requests are answered in order, so several
+        submissions may be outstanding (their waiters must be called in submission order)."""
         used = []
         for i, p in enumerate(self.procs):
             part = tasks[i::len(self.procs)]
@@ -148,14 +153,22 @@ class _DecodeWorkers:
                 p.stdin.write(struct.pack("<I", len(blob)) + blob)
                 p.stdin.flush()
                 used.append(p)
-        err = None
-        for p in used:
-            hdr = p.stdout.read(4)
-            if len(hdr) < 4:
-                raise RuntimeError("a decode worker died (exit code %r)" % p.poll())
-            err = pickle.loads(p.stdout.read(struct.unpack("<I", hdr)[0])) or err
-        if err:
-            raise RuntimeError("decode worker: " + err)
+
+        def wait():
+            err = None
+            for p in used:
+                hdr = p.stdout.read(4)
+                if len(hdr) < 4:
+                    raise RuntimeError("a decode worker died (exit code %r)" % p.poll())
+                err = pickle.loads(p.stdout.read(struct.unpack("<I", hdr)[0])) or err
+            if err:
+                raise RuntimeError("decode worker: " + err)
+
+        return wait
+
+    def drain(self):
+        """After a failed request: stop the workers (later submissions' replies would be mis-paired otherwise)."""
+        self.close()
 
     def close(self):
         for p in self.procs:
@@ -215,8 +228,9 @@ class DeviceDataset:
             yield buf.pop(self._shuffle_rng.randrange(len(buf)))
 
     # -- one batch -----------------------------------------------------------------------------------------------------
-    def _build(self, samples, slot):
-        """samples: list of sample descriptions -> dict of device tensors (work enqueued on self.stream)."""
+    def _begin(self, samples, slot):
+        """First half of a batch: lay the frames out in the slot's staging buffer, hand the JPEGs to the decode workers
+        (not waited for) and build the frame plans while they decode."""
         keys = list(samples[0]["frames"])
         reqs = [r for k in keys for s in samples for r in s["frames"][k]]       # key-major: each key is contiguous
         n = len(reqs)
@@ -225,19 +239,18 @@ class DeviceDataset:
             offs.append(total)
             if not r.get("zero"):
                 total += r["size"][0] * r["size"][1] * 3
-        plans = augment.PlanTable(n, pin=False)
         plan_bytes = n * augment.PLAN_BYTES
         if slot.event is not None:
             slot.event.synchronize()               # the previous batch of this slot has left the staging buffer
         host = slot.reserve(total + plan_bytes + 16)
-        host_np = host.numpy()
-
         live = [i for i in range(n) if not reqs[i].get("zero")]
         if self.decode == "process":
             if self.workers is None:
                 self.workers = _DecodeWorkers(self.n_workers)
-            self.workers.run([(slot.path, offs[i], reqs[i]["path"]) + tuple(reqs[i]["size"]) for i in live])
+            waiter = self.workers.submit([(slot.path, offs[i], reqs[i]["path"]) + tuple(reqs[i]["size"]) for i in live])
         else:
+            host_np = host.numpy()
+
             def work(i):
                 w, h = reqs[i]["size"]
                 px = decode_rgb(reqs[i]["path"])
@@ -245,15 +258,25 @@ class DeviceDataset:
                     raise ValueError("%s: decoded %s, header said %s" % (reqs[i]["path"], px.shape, (h, w, 3)))
                 host_np[offs[i]:offs[i] + px.size] = px.reshape(-1)
 
-            list(self.pool.map(work, live))
-        for i, r in enumerate(reqs):
-            if r.get("zero"):
-                plans.set_zero(i)
-            else:
-                plans.set(i, offs[i], r["size"][0], r["size"][1], r["resize"][0], r["resize"][1], r["crop"][0], r["crop"][1],
-                          r["angle"], r["flip"], r["filter_id"], r["factor"])
+            futures = [self.pool.submit(work, i) for i in live]
+            waiter = lambda: [f.result() for f in futures]      # noqa: E731
+        plans = augment.PlanTable(n, pin=False)
+        plans.set_batch(reqs, offs)                 # one library call (this thread shares the GIL with the consumer)
+        return dict(samples=samples, keys=keys, n=n, total=total, plans=plans, slot=slot, waiter=waiter)
+
+    def _finish(self, pend):
+        """Second half: wait for the decoded frames, then one H2D copy and one kernel launch on the side stream."""
+        samples, keys, n, total, slot = pend["samples"], pend["keys"], pend["n"], pend["total"], pend["slot"]
+        try:
+            pend["waiter"]()
+        except Exception:
+            if self.workers is not None:
+                self.workers.drain()
+                self.workers = None
+            raise
+        plan_bytes = n * augment.PLAN_BYTES
         plan_off = (total + 15) // 16 * 16
-        host[plan_off:plan_off + plan_bytes].copy_(plans.host[:plan_bytes])
+        slot.host[plan_off:plan_off + plan_bytes].copy_(pend["plans"].host[:plan_bytes])
         with torch.cuda.stream(self.stream):
             up = slot.upload_source(plan_off + plan_bytes)
             slot.dev[:plan_off + plan_bytes].copy_(up[:plan_off + plan_bytes], non_blocking=True)
@@ -273,21 +296,30 @@ class DeviceDataset:
         return batch, slot.event, total + plan_bytes
 
     def _batches(self):
+        """Two batches in flight on the host: the decode of batch i+1 is handed to the workers before batch i is waited
+        for, so the workers never idle while this thread draws samples, builds plans or enqueues GPU work."""
         it = self._samples()
         if self.shuffle:
             it = self._shuffled(it)
-        slots = collections.deque(_Staging(self.device) for _ in range(self.prefetch + 2))
+        slots = collections.deque(_Staging(self.device) for _ in range(self.prefetch + 3))
         self._slots.extend(slots)
-        cur = []
+        cur, pending = [], None
         for s in it:
             cur.append(s)
             if len(cur) == self.batch_size:
                 slots.rotate(-1)
-                yield self._build(cur, slots[0])
-                cur = []
+                nxt = self._begin(cur, slots[0])
+                if pending is not None:
+                    yield self._finish(pending)
+                pending, cur = nxt, []
         if cur:
             slots.rotate(-1)
-            yield self._build(cur, slots[0])
+            nxt = self._begin(cur, slots[0])
+            if pending is not None:
+                yield self._finish(pending)
+            pending = nxt
+        if pending is not None:
+            yield self._finish(pending)
 
     def __iter__(self):
         if not self.prefetch:
