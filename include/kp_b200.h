@@ -331,6 +331,12 @@ int kp_augment_plan_batch_host(kp_frame_plan* plans, int n, const long long* src
                                const int* angle_deg, const int* flip, const int* filter_id, const double* factor,
                                const int* zero);
 
+/* HOST functions: page-lock / release a host range the CALLER owns (the loader's staging buffer is a shared mapping its
+ * decode worker processes write into, so it cannot come from cudaHostAlloc).  KP_ERR_CUDA when CUDA refuses; no error
+ * state is left behind in that case.                                                                                */
+int kp_host_register(void* host_ptr, unsigned long long bytes);
+int kp_host_unregister(void* host_ptr);
+
 /* src: device buffer of decoded frames; plans: DEVICE array [n_frames]; out f32 [n_frames,128,128,3] =
  * float32(pixel / 255.0) * 2 - 1 (`image / 255.0` of data/image_pair_dataloader.py:162-165 followed by map_fn :63-69).
  * One launch, byte-exact against Pillow; 49 152 B gathered + 196 608 B written per frame (HBM-bound).               */

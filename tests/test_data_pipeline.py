@@ -126,6 +126,8 @@ def test_plan_builder_rejects_bad_arguments(lib_built):
     assert h.kp_augment_frames(None, None, -1, None, None) == -1
     assert h.kp_augment_frames(None, None, 0, None, None) == 0           # empty batch
     assert h.kp_augment_frames(None, None, 4, None, None) == -1
+    assert h.kp_host_register(None, 16) == -1 and h.kp_host_unregister(None) == -1
+    assert h.kp_augment_plan_batch_host(None, 0, *([None] * 12)) == 0 and h.kp_augment_plan_batch_host(None, 2, *([None] * 12)) == -1
     import torch
     with pytest.raises(ValueError):
         A.augment_frames(torch.zeros(16, dtype=torch.uint8), torch.zeros(568, dtype=torch.uint8), 1)

@@ -67,6 +67,8 @@ SIGNATURES = {
     "kp_augment_plan_zero_host": [c_vp],
     "kp_augment_plan_batch_host": [c_vp, c_int] + [c_vp] * 12,
     "kp_augment_frames": [c_vp, c_vp, c_int, c_vp, c_vp],
+    "kp_host_register": [c_vp, ctypes.c_ulonglong],
+    "kp_host_unregister": [c_vp],
 }
 _RESTYPES = {"kp_last_error": ctypes.c_char_p, "kp_launch_count": ctypes.c_ulonglong}
 

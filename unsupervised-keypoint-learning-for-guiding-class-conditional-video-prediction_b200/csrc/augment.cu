@@ -187,6 +187,28 @@ int kp_augment_plan_batch_host(kp_frame_plan* plans, int n, const long long* src
     return KP_OK;
 }
 
+int kp_host_register(void* host_ptr, unsigned long long bytes) {
+    KP_REQUIRE(host_ptr != nullptr && bytes > 0, "%s: empty range", __func__);
+    const cudaError_t e = cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();      // a refused registration is an answer, not a fault: leave no sticky error behind
+        set_error("%s: cudaHostRegister: %s", __func__, cudaGetErrorString(e));
+        return KP_ERR_CUDA;
+    }
+    return KP_OK;
+}
+
+int kp_host_unregister(void* host_ptr) {
+    KP_REQUIRE(host_ptr != nullptr, "%s: argument 'host_ptr' must not be NULL", __func__);
+    const cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("%s: cudaHostUnregister: %s", __func__, cudaGetErrorString(e));
+        return KP_ERR_CUDA;
+    }
+    return KP_OK;
+}
+
 int kp_augment_frames(const unsigned char* src, const kp_frame_plan* plans, int n_frames, float* out, void* stream) {
     KP_REQUIRE(n_frames >= 0, "%s: argument 'n_frames' must be non-negative", __func__);
     if (n_frames == 0) return KP_OK;

@@ -34,7 +34,7 @@ import numpy as np
 import torch
 from PIL import Image
 
-from .. import augment
+from .. import _lib, augment
 
 IMAGE_SIZE = augment.IMAGE_SIZE
 
@@ -74,6 +74,20 @@ def decode_rgb(path):
         return np.asarray(im if im.mode == "RGB" else im.convert("RGB"))
 
 
+_STAGE_FILES = set()
+
+
+def _unlink_leftovers():
+    for path in list(_STAGE_FILES):
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
+atexit.register(_unlink_leftovers)
+
+
 class _Staging:
     """One batch in flight: frame bytes + plans in a shared, CUDA-registered host mapping (decode workers write into it),
     their device copy, and the event that marks the batch's kernel."""
@@ -94,12 +108,13 @@ class _Staging:
             shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
             self._gen += 1
             self.path = os.path.join(shm, "%s_%d" % (self._stem, self._gen))
+            _STAGE_FILES.add(self.path)
             with open(self.path, "w+b") as fh:
                 fh.truncate(cap)
                 self._mm = mmap.mmap(fh.fileno(), cap)
             self.host = torch.frombuffer(self._mm, dtype=torch.uint8)
-            rc = torch.cuda.cudart().cudaHostRegister(self.host.data_ptr(), cap, 0)
-            self._registered = int(rc) == 0
+            torch.cuda.current_stream(self.device)         # the CUDA context exists before the library registers memory
+            self._registered = _lib.load().kp_host_register(self.host.data_ptr(), cap) == 0
             self._pinned = None if self._registered else torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
         return self.host
@@ -116,16 +131,15 @@ class _Staging:
             if self.event is not None:
                 self.event.synchronize()
             if self._registered:
-                try:
-                    torch.cuda.cudart().cudaHostUnregister(self.host.data_ptr())
-                except Exception:          # interpreter / context teardown
-                    pass
+                _lib.load().kp_host_unregister(self.host.data_ptr())      # status ignored: nothing to do about it here
+                self._registered = False
             self.host = None
         if self.path is not None:
             try:
                 os.unlink(self.path)
             except OSError:
                 pass
+            _STAGE_FILES.discard(self.path)
             self.path = None
 
 
@@ -202,6 +216,7 @@ class DeviceDataset:
         self.pool = concurrent.futures.ThreadPoolExecutor(self.n_workers)
         self.workers = None
         self._slots = []
+        self._producer = None
         self.prefetch = 1 if prefetch else 0
         self.stream = torch.cuda.Stream(device=self.device)
         self.shuffle_buffer = shuffle_buffer
@@ -322,6 +337,8 @@ class DeviceDataset:
             yield self._finish(pending)
 
     def __iter__(self):
+        """One iterator at a time: the staging slots and the decode workers belong to it."""
+        self._stop_producer()
         if not self.prefetch:
             for batch, ev, _ in self._batches():
                 yield self._hand_over(batch, ev)
@@ -329,23 +346,27 @@ class DeviceDataset:
         q = queue.Queue(maxsize=self.prefetch)
         stop = threading.Event()
 
+        def offer(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
         def producer():
             try:
                 with torch.cuda.device(self.device):
                     for item in self._batches():
-                        while not stop.is_set():
-                            try:
-                                q.put(item, timeout=0.1)
-                                break
-                            except queue.Full:
-                                continue
-                        if stop.is_set():
+                        if not offer(item):
                             return
-                q.put(None)
+                offer(None)
             except BaseException as exc:       # surfaces in the consumer
-                q.put(exc)
+                offer(exc)
 
         th = threading.Thread(target=producer, daemon=True)
+        self._producer = (th, stop)
         th.start()
         try:
             while True:
@@ -358,14 +379,26 @@ class DeviceDataset:
         finally:
             stop.set()
 
+    def _stop_producer(self):
+        th, stop = self._producer or (None, None)
+        if th is not None:
+            stop.set()
+            if th is not threading.current_thread():     # the last reference may die on the producer thread itself
+                th.join(timeout=10)
+        self._producer = None
+
     def close(self):
-        """Stop the decode workers and drop the staging mappings (also runs at interpreter exit / garbage collection)."""
-        if self.workers is not None:
-            self.workers.close()
-            self.workers = None
-        for sl in self._slots:
-            sl.release()
-        self._slots = []
+        """Stop the batch-building thread and the decode workers, drop the staging mappings (also runs at garbage
+        collection)."""
+        try:
+            self._stop_producer()
+            if self.workers is not None:
+                self.workers.close()
+                self.workers = None
+        finally:            # whatever happened above, page-locked staging memory must not outlive its mapping
+            for sl in self._slots:
+                sl.release()
+            self._slots = []
 
     def __del__(self):
         try:
