@@ -140,3 +140,23 @@ def test_pseudo_labels_from_the_keypoint_loader(cuda_dev, tmp_path):
         want = model.detect(v["image"][0, :n].contiguous()).cpu().numpy()
         assert np.array_equal(arr, want)
         assert np.all(np.abs(arr) <= 1.0)
+
+
+def test_abandoned_datasets_release_their_staging_memory(cuda_dev, tmp_path):
+    """A data set whose iterator is dropped mid-stream (its last reference then dies on the batch-building thread) must still
+    un-register its page-locked staging mapping: a later mapping at the same address registers cleanly and no CUDA error is
+    left behind."""
+    import gc
+    import time
+    from kp_b200 import data
+    root = DC.lay_out_dataset(tmp_path)
+    ld = data.ImagePairDataLoader(root, "train", random_order=True, randomness=True)
+    for _ in range(4):
+        it = iter(ld.get_dataset(batch_size=2, repeat=True, num_preprocess_threads=2, device=cuda_dev))
+        b = next(it)
+        assert b["image"].shape == (2, 128, 128, 3)
+        del it, b
+        gc.collect()
+        time.sleep(0.3)                     # the producer notices the stop flag within 0.1 s and lets go of the data set
+    torch.cuda.synchronize()
+    assert float(torch.empty(4, device=cuda_dev).fill_(1).sum()) == 4.0
