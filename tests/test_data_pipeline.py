@@ -240,3 +240,36 @@ def test_decode_workers_write_identical_bytes_and_surface_errors(lib_built, tmp_
             W.run([(stage, 0, paths[0], 5, 5)])
     finally:
         W.close()
+
+
+def test_edge_geometries_kernel_arithmetic_vs_oracle_vs_pillow(lib_built):
+    """Frames smaller than the crop (up-scaling), square, extreme aspect ratios, crops partly or wholly outside the frame:
+    Pillow itself, the oracle and the kernel's phases (host build + the product's plan builder) agree byte for byte."""
+    rng = np.random.default_rng(11)
+    cases = [(100, 80), (80, 100), (128, 128), (64, 64), (640, 129), (129, 640), (1, 1), (3, 200), (255, 257)]
+    frames, reqs, pil_out = [], [], []
+    for i, (w, h) in enumerate(cases):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        W, H, _ = O.resized_size(w, h)
+        for crop in [(0, 0), (W / 2.0 - 64, 0), (W - 100, H - 90), (-200, -200), (0.5, 1.5)]:
+            ang = int(rng.integers(-10, 11))
+            flip = int(rng.integers(0, 2))
+            fid = int(rng.integers(-1, 10))
+            fac = float(rng.integers(0, 51)) * 0.1
+            frames.append(img)
+            reqs.append({"resize": (W, H), "crop": crop, "angle": ang, "flip": flip, "filter_id": fid, "factor": fac})
+            pil = Image.fromarray(img).rotate(ang).resize([W, H], Image.NEAREST)
+            pil = pil.crop((crop[0], crop[1], crop[0] + 128, crop[1] + 128))
+            if flip:
+                pil = pil.transpose(Image.FLIP_LEFT_RIGHT)
+            if 0 <= fid <= 5:
+                pil = pil.filter([ImageFilter.DETAIL, ImageFilter.EDGE_ENHANCE, ImageFilter.SMOOTH, ImageFilter.SMOOTH_MORE,
+                                  ImageFilter.EDGE_ENHANCE_MORE, ImageFilter.BLUR][fid])
+            elif fid >= 6:
+                pil = [ImageEnhance.Sharpness, ImageEnhance.Brightness, ImageEnhance.Color, ImageEnhance.Contrast][fid - 6](pil).enhance(fac)
+            pil_out.append(O.to_model_range(np.asarray(pil)))
+    got = DC.emulate(frames, reqs)
+    for i, (f, r) in enumerate(zip(frames, reqs)):
+        want = DC.oracle_frame(f, r)
+        assert np.array_equal(want, pil_out[i]), ("oracle vs Pillow", f.shape, r)
+        assert np.array_equal(got[i], want), ("kernel phases vs oracle", f.shape, r)
