@@ -739,12 +739,20 @@ def bench_input(args, dev, lib, peaks):
     ms_plain = ev0.elapsed_time(ev1) / steps
     del src, out
     achieved = INPUT_BYTES_PER_FRAME * n / (ms * 1e-3) / 1e9
+    traffic, tsrc = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "input_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("frames_per_launch") == n:      # the capture is of this launch size
+            traffic, tsrc = tj["dram_bytes_per_launch"], tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     sub = {"workload": "input pipeline of the stage-1 loaders (data/image_pair_dataloader.py:72-165): rotate + resize + crop + flip "
                        "+ random filter + normalise of %d decoded 320x240 frames per launch, random plans as the reference draws them" % n,
            "frames_per_s": n / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "gpu_launches": launches, "dtype": "u8",
            "l2": "decoded frames %d MB + output %d MB per launch >> 126 MB L2" % (n * w * h * 3 >> 20, n * 196608 >> 20),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                        "traffic": None, "peak_source": peaks["source"], "kernel": "kp::augment_kernel",
+                        "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["source"], "kernel": "kp::augment_kernel",
                         "algorithmic_bytes_per_launch": INPUT_BYTES_PER_FRAME * n},
            "resize_crop_only": {"note": "the keypoint loader's plan (no rotation, no filter), same frames", "ms_per_step": ms_plain,
                                 "frames_per_s": n / (ms_plain * 1e-3), "gbs": INPUT_BYTES_PER_FRAME * n / (ms_plain * 1e-3) / 1e9,
