@@ -692,6 +692,23 @@ def _train_from_files(args, dev, root):
                     "kernel, shuffle buffer) - two batches per step, losses D2H every step" % (B, ds.n_workers)}
 
 
+def _with_deadline(seconds, fn, *a):
+    """Run a sub-benchmark that talks to worker processes under an alarm, so that a stuck pipe cannot take the headline line
+    with it (main thread only; blocking queue / pipe reads are interrupted by the signal)."""
+    import signal
+
+    def on_alarm(signum, frame):
+        raise TimeoutError("sub-benchmark exceeded %d s" % seconds)
+
+    old = signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(seconds)
+    try:
+        return fn(*a)
+    finally:
+        signal.alarm(0)
+        signal.signal(signal.SIGALRM, old)
+
+
 def bench_input(args, dev, lib, peaks):
     """Input pipeline: kp_augment_frames on frames resident in HBM (roofline: HBM), the loader end to
     end from JPEG files (PIL decode on host threads -> pinned staging -> H2D -> one launch per batch), and the reference's
@@ -946,7 +963,7 @@ def run_ours(args):
         if not args.no_k1:
             subs["k1"] = bench_k1(args, world, rank, dev, lib)
         try:
-            subs["input"] = bench_input(args, dev, lib, peaks)
+            subs["input"] = _with_deadline(180, bench_input, args, dev, lib, peaks)
         except Exception as e:
             subs["input"] = {"error": repr(e)}
         torch.cuda.empty_cache()

@@ -273,3 +273,17 @@ def test_edge_geometries_kernel_arithmetic_vs_oracle_vs_pillow(lib_built):
         want = DC.oracle_frame(f, r)
         assert np.array_equal(want, pil_out[i]), ("oracle vs Pillow", f.shape, r)
         assert np.array_equal(got[i], want), ("kernel phases vs oracle", f.shape, r)
+
+
+def test_keypoint_loader_shards_cover_the_video_list_once(lib_built, tmp_path):
+    """make_pseudo_labels over N ranks: the loader's sample_range shards (dp.shard_range) are disjoint and complete."""
+    from kp_b200 import data, dp
+    root = DC.lay_out_dataset(tmp_path)
+    kl = data.KeypointDataLoader(root, "test")
+    everything = [s["extra"]["idx"] for s in kl.sample_generator()]
+    for world in (1, 2, 3, 4, 7):
+        seen = []
+        for rank in range(world):
+            lo, hi = dp.shard_range(kl.length(), rank, world)
+            seen += [s["extra"]["idx"] for s in kl.sample_generator(lo, hi)]
+        assert seen == everything, world
