@@ -9,7 +9,7 @@ import torch
 
 import data_common as DC
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(240)]      # worker processes and pipes: fail, never hang
 
 SIZES = [(320, 240), (240, 320), (200, 200), (480, 270), (157, 131), (131, 157), (129, 640)]
 
